@@ -1,0 +1,132 @@
+"""Drop-in for models/armnet.py (multi-head ARM-Net): same constructor signature, parameter names/shapes/init
+order and forward contract as the reference's SparseAttLayer / ARMNetModel (armnet.py:8-101); the hot path
+(value clamp, embedding lookup, attention logits, entmax gates, exponential-neuron interaction) runs in the fused
+sm_100a kernel behind armnet_fused_fwd_f32."""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .layers import MLP, Embedding
+
+
+class SparseAttLayer(nn.Module):
+    """Parameters of the multi-head sparse attention (armnet.py:9-24). forward() is the unfused composition used
+    when autograd is recording: logits by cuBLAS einsum, gates by the CUDA entmax op (with its backward)."""
+
+    def __init__(self, nhead, nfield, nemb, d_k, nhid, alpha=1.5):
+        super().__init__()
+        self.alpha = alpha
+        self.scale = d_k ** -0.5
+        self.bilinear_w = nn.Parameter(torch.zeros(nhead, nemb, d_k))
+        self.query = nn.Parameter(torch.zeros(nhead, nhid, d_k))
+        self.values = nn.Parameter(torch.zeros(nhead, nhid, nfield))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.xavier_uniform_(self.bilinear_w, gain=1.414)
+        nn.init.xavier_uniform_(self.query, gain=1.414)
+        nn.init.xavier_uniform_(self.values, gain=1.414)
+
+    def forward(self, x):
+        """x [B,F,E] -> gates*values [B,K,O,F] (armnet.py:26-36)."""
+        g = torch.einsum('bfx,kxy,koy->bkof', x, self.bilinear_w, self.query) * self.scale
+        p = ops.entmax(g, alpha=self.alpha, dim=-1)
+        return torch.einsum('bkof,kof->bkof', p, self.values)
+
+
+class _PaddedTable:
+    """16-byte-aligned shadow of an embedding table whose rows are not (nemb % 4 != 0, e.g. 40-byte rows at
+    nemb=10), so the kernel can fetch rows with TMA bulk copies. Rebuilt when the parameter changes."""
+
+    def __init__(self):
+        self.key = None
+        self.buf = None
+
+    def get(self, weight):
+        E = weight.shape[1]
+        if E % 4 == 0:
+            return weight, E
+        key = (weight.data_ptr(), weight._version, weight.device)
+        if key != self.key:
+            ld = (E + 3) // 4 * 4
+            buf = torch.zeros(weight.shape[0], ld, dtype=weight.dtype, device=weight.device)
+            buf[:, :E] = weight.detach()
+            self.key, self.buf = key, buf
+        return self.buf, self.buf.shape[1]
+
+
+class ARMNetModel(nn.Module):
+    """Adaptive Relation Modeling Network, multi-head (armnet.py:39-101)."""
+
+    one_head = False
+
+    def __init__(self, nfield, nfeat, nemb, nhead, alpha, nhid, mlp_nlayer, mlp_nhid, dropout, ensemble,
+                 deep_nlayer, deep_nhid, noutput=1):
+        super().__init__()
+        self.alpha = alpha
+        # same construction order as the reference => same parameters under the same seed
+        self.embedding = Embedding(nfeat, nemb)
+        self.attn_layer = SparseAttLayer(nhead, nfield, nemb, nemb, nhid, alpha)
+        self.arm_bn = nn.BatchNorm1d(nhead * nhid)
+        self.mlp = MLP(nhead * nhid * nemb, mlp_nlayer, mlp_nhid, dropout, noutput=noutput)
+        if ensemble:
+            self.deep_embedding = Embedding(nfeat, nemb)
+            self.deep_mlp = MLP(nfield * nemb, deep_nlayer, deep_nhid, dropout, noutput=noutput)
+            self.ensemble_layer = nn.Linear(2 * noutput, 1 * noutput)
+            nn.init.constant_(self.ensemble_layer.weight, 0.5)
+            nn.init.constant_(self.ensemble_layer.bias, 0.)
+        # host-side knobs (not parameters, not in state_dict)
+        self.padded_table = True     # keep a 16-byte-aligned shadow table for TMA row gathers in no-grad mode
+        self.validate_ids = False    # synchronising id-range check after each forward (reference: IndexError)
+        self.solver = ops.SOLVER_AUTO
+        self._shadow = _PaddedTable()
+        self._err_flag = None
+
+    # ------------------------------------------------------------------ hot path
+    def _attn_weights(self):
+        a = self.attn_layer
+        return a.bilinear_w, a.query, a.values
+
+    def interaction(self, x, **want):
+        """Fused hot path (armnet.py:82-87): returns z [B, K*O, E] (+ optional stage outputs)."""
+        table = self.embedding.embedding.weight
+        if self.padded_table:
+            tab, ld = self._shadow.get(table)
+        else:
+            tab, ld = table.detach(), table.shape[1]
+        W, Q, Vv = self._attn_weights()
+        if self.validate_ids and (self._err_flag is None or self._err_flag.device != table.device):
+            self._err_flag = ops.new_error_flag(table.device)
+        z, extra = ops.fused_forward(x['id'], x['value'], tab, W.detach(), Q.detach(), Vv.detach(), self.alpha,
+                                     one_head=self.one_head, solver=self.solver, ld=ld, nemb=table.shape[1],
+                                     err_flag=self._err_flag if self.validate_ids else None, **want)
+        if self.validate_ids:
+            ops.raise_if_bad_ids(self._err_flag)
+        return (z, extra) if want else z
+
+    def _interaction_autograd(self, x):
+        """Same stages with autograd recording (training): CUDA gather + cuBLAS einsums + CUDA entmax fwd/bwd."""
+        x['value'].clamp_(0.001, 1.)
+        e = self.embedding(x)
+        w = self.attn_layer(e)
+        z = torch.exp(torch.einsum('bfe,bkof->bkoe', e, w))
+        return z.reshape(z.shape[0], -1, z.shape[-1])
+
+    def _needs_grad(self):
+        return torch.is_grad_enabled() and (self.embedding.embedding.weight.requires_grad or
+                                            any(p.requires_grad for p in self.attn_layer.parameters()))
+
+    def forward(self, x):
+        """x = {'id': Long[B,F], 'value': Float[B,F]} -> y [B] (0-dim when B == 1). Clamps x['value'] in place."""
+        if not x['value'].is_cuda:
+            raise RuntimeError('armnet_b200.ARMNetModel runs on CUDA only (no CPU fallback): move the model and the '
+                               'batch to a B200')
+        z = self._interaction_autograd(x) if self._needs_grad() else self.interaction(x)
+        B = z.shape[0]
+        x_arm = self.arm_bn(z).reshape(B, -1)
+        y = self.mlp(x_arm)
+        if hasattr(self, 'ensemble_layer'):
+            x_deep = self.deep_embedding(x).reshape(B, -1)
+            y_deep = self.deep_mlp(x_deep)
+            y = self.ensemble_layer(torch.cat([y, y_deep], dim=1))
+        return y.squeeze()

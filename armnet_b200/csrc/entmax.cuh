@@ -1,0 +1,141 @@
+// Per-row alpha-entmax threshold solvers, one row of FP (padded) logits held in one thread's registers.
+//
+// Reference: utils/entmax.py:29-68 finds tau with 50 bisection halvings of [max-1, max-(1/d)^(alpha-1)]
+// and returns p = [X - tau]_+^(1/(alpha-1)) / sum.  In fp32 that bisection reaches a bitwise fixed point after
+// 20-40 halvings; any converged root-finder lands inside the reference's own fp32-vs-fp64 noise
+// (tools/entmax_newton_proto.py, DESIGN.md "entmax").  The solvers here:
+//   POW_GENERAL (1<alpha<2): f(tau) = sum u^q - 1 is convex and decreasing, so Newton from a lower bound
+//       converges monotonically. Start at max(max-1, mean - F^-(alpha-1)) (max-element bound and Jensen bound);
+//       u^(q-1) = ex2((q-1) lg2 u) gives f' and, times u, f: two MUFU per element per pass.
+//   POW_SQUARE  (alpha=1.5): same Newton with u^2 / u, no MUFU.
+//   POW_LINEAR  (alpha=2)  : Michelot's iteration tau += (sum u - 1)/|support| (Newton on a piecewise-linear f).
+//   POW_BISECT  : the reference's loop, literally, with exit at the fixed point tau_lo + dm == tau_lo.
+//   POW_SOFTMAX (alpha=1)  : tau := max, p = exp(X - max).
+// Every solver returns tau; the caller evaluates p_f = pow_mode(X_f, tau) and divides by their sum, which is the
+// reference's final renormalisation (entmax.py:63-64).
+#pragma once
+
+#include "common.cuh"
+
+namespace armnet {
+
+__device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+
+// Unnormalised gate for one element, given the solved tau (mode is warp-uniform).
+template <int MODE>
+__device__ __forceinline__ float gate_unnorm(float x, float tau, const EntmaxParams &ep) {
+    if (MODE == POW_SOFTMAX) {
+        return fast_ex2((x - tau) * 1.4426950408889634f);
+    } else if (MODE == POW_LINEAR) {
+        return fmaxf(x - tau, 0.f);
+    } else if (MODE == POW_SQUARE) {
+        const float u = fmaxf(x - tau, 0.f);
+        return u * u;
+    } else {  // POW_GENERAL, POW_BISECT: u^q, u = 0 -> lg2 = -inf -> ex2(-inf) = 0
+        const float u = fmaxf(x - tau, 0.f);
+        return fast_ex2(ep.q * fast_lg2(u));
+    }
+}
+
+// Runtime-mode variant for cold paths (debug outputs, standalone kernels' epilogues).
+__device__ __forceinline__ float gate_unnorm_rt(float x, float tau, const EntmaxParams &ep) {
+    switch (ep.mode) {
+        case POW_SOFTMAX: return gate_unnorm<POW_SOFTMAX>(x, tau, ep);
+        case POW_LINEAR: return gate_unnorm<POW_LINEAR>(x, tau, ep);
+        case POW_SQUARE: return gate_unnorm<POW_SQUARE>(x, tau, ep);
+        default: return gate_unnorm<POW_GENERAL>(x, tau, ep);
+    }
+}
+
+// X[f] = (alpha-1) * g[f] for f < F (g itself for softmax), -inf for padded f >= F.
+// All 32 lanes of the warp must call this together (warp-uniform exit votes).
+template <int FP, bool EXACT>
+__device__ __forceinline__ float entmax_solve_tau(const float (&X)[FP], int F, const EntmaxParams &ep) {
+    float mx = X[0];
+#pragma unroll
+    for (int f = 1; f < FP; ++f) mx = fmaxf(mx, X[f]);
+    if (ep.mode == POW_SOFTMAX) return mx;
+
+    if (ep.mode == POW_BISECT) {
+        // entmax.py:46-61, step by step.
+        float tau_lo = mx - 1.f;
+        const float tau_hi = mx - ep.cF;
+        float f_lo = 0.f;
+#pragma unroll
+        for (int f = 0; f < FP; ++f) f_lo += gate_unnorm<POW_BISECT>(X[f], tau_lo, ep);
+        f_lo -= 1.f;
+        float dm = tau_hi - tau_lo;
+        float tau_m = tau_lo;
+        for (int it = 0; it < ep.n_iter; ++it) {
+            dm *= 0.5f;
+            tau_m = tau_lo + dm;
+            // fixed point: every later midpoint equals tau_lo, so every later p_m equals this one
+            const bool fixed = (tau_m == tau_lo);
+            float s = 0.f;
+#pragma unroll
+            for (int f = 0; f < FP; ++f) s += gate_unnorm<POW_BISECT>(X[f], tau_m, ep);
+            const float f_m = s - 1.f;
+            if (f_m * f_lo >= 0.f) tau_lo = tau_m;
+            if (__all_sync(0xffffffffu, fixed)) break;
+        }
+        return tau_m;
+    }
+
+    // Lower bounds on the root: the max element alone gives tau >= max - 1; Jensen on the convex u^q
+    // (q >= 1) gives tau >= mean - F^-(1/q) = mean - F^-(alpha-1).
+    float sum = 0.f;
+#pragma unroll
+    for (int f = 0; f < FP; ++f)
+        if (EXACT || f < F) sum += X[f];
+    float tau = fmaxf(mx - 1.f, sum * ep.inv_F - ep.cF);
+
+    constexpr int kMaxIt = 12;
+    if (ep.mode == POW_GENERAL) {
+        const float qm1 = ep.qm1;
+        for (int it = 0; it < kMaxIt; ++it) {
+            float s = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int f = 0; f < FP; ++f) {
+                const float u = fmaxf(X[f] - tau, 0.f);
+                const float w = fast_ex2(qm1 * fast_lg2(u));  // u^(q-1); u = 0 -> 0 because q-1 > 0
+                s1 += w;
+                s = fmaf(w, u, s);
+            }
+            float d = __fdividef(s - 1.f, ep.q * s1);
+            if (!(s1 > 0.f)) d = 0.f;
+            tau += d;  // the step is applied even when it is the last: |f(tau+d)| = O(d^2), and the caller renormalises
+            if (__all_sync(0xffffffffu, fabsf(d) <= 2e-5f)) break;
+        }
+    } else if (ep.mode == POW_SQUARE) {
+        for (int it = 0; it < kMaxIt; ++it) {
+            float s = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int f = 0; f < FP; ++f) {
+                const float u = fmaxf(X[f] - tau, 0.f);
+                s1 += u;
+                s = fmaf(u, u, s);
+            }
+            float d = __fdividef(s - 1.f, 2.f * s1);
+            if (!(s1 > 0.f)) d = 0.f;
+            tau += d;
+            if (__all_sync(0xffffffffu, fabsf(d) <= 2e-5f)) break;
+        }
+    } else {  // POW_LINEAR
+        for (int it = 0; it < kMaxIt; ++it) {
+            float s = 0.f, cnt = 0.f;
+#pragma unroll
+            for (int f = 0; f < FP; ++f) {
+                const float u = X[f] - tau;
+                s += fmaxf(u, 0.f);
+                cnt += (u > 0.f) ? 1.f : 0.f;
+            }
+            float d = __fdividef(s - 1.f, cnt);
+            if (!(cnt > 0.f)) d = 0.f;
+            tau += d;
+            if (__all_sync(0xffffffffu, fabsf(d) <= 2.4e-7f * fmaxf(1.f, fabsf(tau)))) break;
+        }
+    }
+    return tau;
+}
+
+}  // namespace armnet

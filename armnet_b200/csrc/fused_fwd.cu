@@ -1,0 +1,225 @@
+// armnet_fused_fwd_f32: host side of the fused forward (instance selection, launch geometry, parameter
+// pre-contraction).  Kernel: fused_fwd.cuh.  Instances: fused_fwd_inst_*.cu.
+#include <math.h>
+
+#include "fused_fwd.cuh"
+
+namespace armnet {
+
+// Tables of compiled shapes, one per translation unit so they build in parallel.
+extern const FwdInstance kFwdInstancesA[];
+extern const int kNumFwdInstancesA;
+extern const FwdInstance kFwdInstancesB[];
+extern const int kNumFwdInstancesB;
+extern const FwdInstance kFwdInstancesC[];
+extern const int kNumFwdInstancesC;
+extern const FwdInstance kFwdInstancesD[];
+extern const int kNumFwdInstancesD;
+
+static const FwdInstance *select_instance(int F, int E) {
+    const FwdInstance *tabs[] = {kFwdInstancesA, kFwdInstancesB, kFwdInstancesC, kFwdInstancesD};
+    const int ns[] = {kNumFwdInstancesA, kNumFwdInstancesB, kNumFwdInstancesC, kNumFwdInstancesD};
+    const FwdInstance *best = nullptr;
+    long best_cost = 0;
+    for (int t = 0; t < 4; ++t) {
+        for (int i = 0; i < ns[t]; ++i) {
+            const FwdInstance &I = tabs[t][i];
+            if (I.exact ? (I.FP != F) : (I.FP < F)) continue;
+            if (I.EC * I.ES < E) continue;
+            // padded fields cost entmax passes, padded embedding lanes cost FMAs, splitting a row costs shuffles
+            const long cost = (long)I.FP * 10000 + (long)I.EC * I.ES * 10 + I.ES - (I.exact ? 1 : 0);
+            if (!best || cost < best_cost) {
+                best = &I;
+                best_cost = cost;
+            }
+        }
+    }
+    return best;
+}
+
+// M[x][r] = sum_y W[k,x,y] Q[k,o,y] (armnet.py:33: 'bfx,kxy,koy->bkof' contracted over y first; one-head:
+// keys = e W_lin^T then keys.Q, armnet_1h.py:30-31, i.e. W[x,y] = W_lin[y,x]); rows x >= E are zero.
+// Vt[f][r] = att_values[r][f].
+__global__ void attn_prepare_kernel(const float *__restrict__ W, const float *__restrict__ Q,
+                                    const float *__restrict__ Vals, int lin_layout, int F, int E, int D, int O, int R,
+                                    int E_pad, float *__restrict__ Mg, float *__restrict__ Vtg) {
+    const int nM = E_pad * R;
+    const int total = nM + F * R;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        if (i < nM) {
+            const int x = i / R, r = i - x * R;
+            float a = 0.f;
+            if (x < E) {
+                const int k = r / O;
+                const float *q = Q + (long long)r * D;
+                if (lin_layout) {
+                    for (int y = 0; y < D; ++y) a = fmaf(W[y * E + x], q[y], a);
+                } else {
+                    const float *w = W + ((long long)k * E + x) * D;
+                    for (int y = 0; y < D; ++y) a = fmaf(w[y], q[y], a);
+                }
+            }
+            Mg[i] = a;
+        } else {
+            const int j = i - nM;
+            const int f = j / R, r = j - f * R;
+            Vtg[j] = Vals[(long long)r * F + f];
+        }
+    }
+}
+
+static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+}  // namespace armnet
+
+extern "C" size_t armnet_fused_workspace_bytes(int F, int E, int K, int O) {
+    using namespace armnet;
+    if (F <= 0 || E <= 0 || K <= 0 || O <= 0) return 0;
+    const FwdInstance *I = select_instance(F, E);
+    if (!I) return 0;
+    const size_t R = (size_t)K * O;
+    return ((size_t)I->EC * I->ES * R + (size_t)F * R) * sizeof(float);
+}
+
+extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V,
+                                    int64_t ld, const float *bilinear_w, const float *query, const float *att_values,
+                                    int w_is_linear_layout, float alpha, int solver, int n_iter, int64_t B, int F,
+                                    int E, int D, int K, int O, int clamp, float clamp_lo, float clamp_hi,
+                                    int clamp_inplace, float *out_z, float *out_tau, float *out_p, float *out_g,
+                                    float *out_s, void *workspace, int *err_flag, void *stream) {
+    using namespace armnet;
+    note_launches(0);
+    if (!ids || !values || !table || !bilinear_w || !query || !att_values || !out_z || !workspace) {
+        set_error("fused_fwd: null pointer");
+        return ARMNET_ERR_NULL;
+    }
+    if (V <= 0 || B < 0 || F <= 0 || E <= 0 || D <= 0 || K <= 0 || O <= 0 || ld < E ||
+        (w_is_linear_layout && K != 1) || B * (int64_t)K * O > (int64_t)1 << 40) {
+        set_error("fused_fwd: bad shape V=%lld ld=%lld B=%lld F=%d E=%d D=%d K=%d O=%d", (long long)V, (long long)ld,
+                  (long long)B, F, E, D, K, O);
+        return ARMNET_ERR_SHAPE;
+    }
+    if ((uintptr_t)workspace % 16 || (uintptr_t)table % 4 || (uintptr_t)out_z % 4 || (uintptr_t)values % 4 ||
+        (uintptr_t)ids % (ids_i32 ? 4 : 8)) {
+        set_error("fused_fwd: misaligned pointer");
+        return ARMNET_ERR_ALIGN;
+    }
+    const FwdInstance *I = select_instance(F, E);
+    if (!I) {
+        set_error("fused_fwd: no compiled kernel instance for F=%d E=%d (F <= 64, E <= 128 in this build)", F, E);
+        return ARMNET_ERR_UNSUPPORTED;
+    }
+    FwdParams P;
+    int rc = make_entmax_params(alpha, F, solver, n_iter, &P.ep);
+    if (rc != ARMNET_OK) return rc;
+    if (B == 0) return ARMNET_OK;
+    DeviceInfo di;
+    rc = get_device_info(&di);
+    if (rc != ARMNET_OK) return rc;
+
+    const int R = K * O;
+    const int E_pad = I->EC * I->ES;
+    const int ES = I->ES;
+    float *Mg = (float *)workspace;
+    float *Vtg = Mg + (size_t)E_pad * R;
+
+    P.ids = ids;
+    P.values = values;
+    P.table = table;
+    P.Mg = Mg;
+    P.Vtg = Vtg;
+    P.out_z = out_z;
+    P.out_tau = out_tau;
+    P.out_p = out_p;
+    P.out_g = out_g;
+    P.out_s = out_s;
+    P.err_flag = err_flag;
+    P.V = V;
+    P.ld = ld;
+    P.B = B;
+    P.F = F;
+    P.E = E;
+    P.R = R;
+    P.ids_i32 = ids_i32;
+    P.clamp = clamp;
+    P.clamp_inplace = clamp_inplace;
+    P.clamp_lo = clamp_lo;
+    P.clamp_hi = clamp_hi;
+    P.scale = (float)pow((double)D, -0.5);  // armnet.py:15 `d_k ** -0.5`, rounded to fp32 at use (:34)
+
+    // ---- launch geometry: NT consumer threads, TS samples per tile
+    const long long items = (long long)R * ES;  // threads one sample occupies
+    int best_nt = 0, best_ts = 1;
+    double best_eff = -1.0;
+    for (int nt = kMaxConsumerThreads; nt >= 64; nt -= 32) {
+        double eff;
+        int ts;
+        if (items >= nt) {
+            ts = 1;
+            const long long passes = (items + nt - 1) / nt;
+            eff = (double)items / (double)(passes * nt);
+        } else {
+            ts = (int)(nt / items);
+            eff = (double)(ts * items) / nt;
+        }
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best_nt = nt;
+            best_ts = ts;
+        }
+    }
+    long long ts_cap = (B + di.sm_count - 1) / di.sm_count;  // keep every SM busy on small batches
+    if (ts_cap < 1) ts_cap = 1;
+    if (best_ts > ts_cap) {
+        best_ts = (int)ts_cap;
+        const int need = round_up((int)(best_ts * items), 32);
+        if (need < best_nt) best_nt = need < 64 ? 64 : need;
+    }
+    P.NT = best_nt;
+    P.TS = best_ts;
+
+    // ---- TMA eligibility
+    P.row_bytes = round_up(E * 4, 16);
+    P.tma_gather = ((ld * 4) % 16 == 0 && (uintptr_t)table % 16 == 0 && P.row_bytes <= ld * 4) ? 1 : 0;
+    const int rpp = P.NT / ES;
+    P.tma_store = (((long long)R * E) % 4 == 0 && ((long long)rpp * E) % 4 == 0 && (uintptr_t)out_z % 16 == 0) ? 1 : 0;
+
+    // ---- shared-memory budget: drop a pipeline stage, then shrink the tile
+    P.n_stages = kMaxStages;
+    for (;;) {
+        const SmemLayout L(I->FP, E_pad, ES, P);
+        if (L.total <= di.smem_optin) break;
+        if (P.n_stages > 2) {
+            P.n_stages--;
+        } else if (P.TS > 1) {
+            P.TS = (P.TS + 1) / 2;
+        } else {
+            set_error("fused_fwd: F=%d E=%d K*O=%d needs %d bytes of shared memory per CTA (limit %d)", F, E, R, L.total,
+                      di.smem_optin);
+            return ARMNET_ERR_UNSUPPORTED;
+        }
+    }
+    const SmemLayout L(I->FP, E_pad, ES, P);
+    const long long n_tiles = (B + P.TS - 1) / P.TS;
+    if (n_tiles > 0x7fffffffLL) {
+        set_error("fused_fwd: batch too large");
+        return ARMNET_ERR_SHAPE;
+    }
+    P.n_tiles = (int)n_tiles;
+    const unsigned grid = (unsigned)(n_tiles < di.sm_count ? n_tiles : di.sm_count);
+
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        const int total = E_pad * R + F * R;
+        int blocks = (total + 255) / 256;
+        if (blocks > di.sm_count * 4) blocks = di.sm_count * 4;
+        attn_prepare_kernel<<<blocks, 256, 0, st>>>(bilinear_w, query, att_values, w_is_linear_layout, F, E, D, O, R,
+                                                     E_pad, Mg, Vtg);
+        ARMNET_CUDA_TRY(cudaGetLastError());
+    }
+    ARMNET_CUDA_TRY(cudaFuncSetAttribute(I->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
+    void *args[] = {(void *)&P};
+    ARMNET_CUDA_TRY(cudaLaunchKernel(I->kernel, dim3(grid), dim3(P.NT + kProducerThreads), args, (size_t)L.total, st));
+    note_launches(2);
+    return ARMNET_OK;
+}

@@ -1,0 +1,183 @@
+"""torch-facing wrappers of the C ABI (include/armnet_b200.h): device pointers in, torch tensors out.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); the arithmetic of the hot path runs in
+libarmnet_b200.so.  Every op raises on CPU tensors -- there is no fallback path.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _capi
+from ._capi import SOLVER_AUTO, SOLVER_BISECT, check, lib
+
+__all__ = ['embed_gather', 'entmax', 'fused_forward', 'new_error_flag', 'raise_if_bad_ids',
+           'SOLVER_AUTO', 'SOLVER_BISECT', 'last_launch_count']
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('armnet_b200 ops run on CUDA tensors only (no CPU fallback); got a '
+                               f'{t.device} tensor')
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ids_arg(ids):
+    if ids.dtype == torch.int64:
+        return 0
+    if ids.dtype == torch.int32:
+        return 1
+    raise TypeError(f'ids must be int64 or int32, got {ids.dtype}')
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32:
+        raise TypeError(f'{name} must be float32, got {t.dtype}')
+    return t.contiguous()
+
+
+def new_error_flag(device):
+    """Device word the kernels OR bit 0 into when they meet an id outside [0, nfeat)."""
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def raise_if_bad_ids(flag):
+    """Synchronising check of an error flag; mirrors nn.Embedding's IndexError (layers.py:20)."""
+    if int(flag.item()) & 1:
+        flag.zero_()
+        raise IndexError('index out of range in self (armnet_b200: id outside [0, nfeat))')
+
+
+def last_launch_count():
+    return lib.armnet_last_launch_count()
+
+
+def _values_inplace(values):
+    """The reference clamps the caller's tensor in place (armnet.py:82). For a contiguous fp32 tensor the kernel
+    writes into it directly; otherwise clamp with torch first and hand the kernel a contiguous copy."""
+    if values.dtype == torch.float32 and values.is_contiguous():
+        return values, True
+    raise TypeError('values must be a contiguous float32 tensor')
+
+
+def embed_gather(ids, values, table, clamp: Optional[Tuple[float, float]] = None, clamp_inplace=True,
+                 ld: Optional[int] = None, nemb: Optional[int] = None, err_flag=None):
+    """layers.Embedding.forward (layers.py:15-21) [+ the value clamp of armnet.py:82 when clamp=(lo, hi)].
+    ids [B,F] int64/int32, values [B,F] f32, table [V, ld] f32 -> [B,F,E] f32 (bit-exact vs the reference)."""
+    _need_cuda(ids, values, table)
+    ids_c = ids.contiguous()
+    values, _ = _values_inplace(values)
+    table = _f32c(table, 'table')
+    V = table.shape[0]
+    ld = table.shape[1] if ld is None else ld
+    E = table.shape[1] if nemb is None else nemb
+    B, F = ids_c.shape
+    out = torch.empty(B, F, E, dtype=torch.float32, device=table.device)
+    lo, hi = clamp if clamp is not None else (0.0, 0.0)
+    rc = lib.armnet_embed_gather_f32(ids_c.data_ptr(), _ids_arg(ids_c), values.data_ptr(), table.data_ptr(), V, ld,
+                                     B, F, E, out.data_ptr(), int(clamp is not None), lo, hi, int(clamp_inplace),
+                                     err_flag.data_ptr() if err_flag is not None else None, _stream())
+    check(rc, 'armnet_embed_gather_f32')
+    return out
+
+
+def entmax_forward(x, alpha, n_iter=50, solver=SOLVER_AUTO):
+    """Row-wise alpha-entmax over the last axis of a contiguous fp32 CUDA tensor (entmax.py:29-68)."""
+    _need_cuda(x)
+    x = _f32c(x, 'x')
+    F = x.shape[-1]
+    rows = x.numel() // F if F else 0
+    p = torch.empty_like(x)
+    check(lib.armnet_entmax_f32(x.data_ptr(), rows, F, float(alpha), solver, n_iter, p.data_ptr(), _stream()),
+          'armnet_entmax_f32')
+    return p
+
+
+def entmax_backward(p, dp, alpha):
+    """EntmaxBisectFunction.backward (entmax.py:71-80)."""
+    _need_cuda(p, dp)
+    p = _f32c(p, 'p')
+    dp = _f32c(dp, 'dp')
+    F = p.shape[-1]
+    rows = p.numel() // F if F else 0
+    dx = torch.empty_like(p)
+    check(lib.armnet_entmax_bwd_f32(p.data_ptr(), dp.data_ptr(), rows, F, float(alpha), dx.data_ptr(), _stream()),
+          'armnet_entmax_bwd_f32')
+    return dx
+
+
+class _EntmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, alpha, n_iter, solver):
+        p = entmax_forward(x, alpha, n_iter, solver)
+        ctx.alpha = alpha
+        ctx.save_for_backward(p)
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        p, = ctx.saved_tensors
+        return entmax_backward(p, dp.contiguous(), ctx.alpha), None, None, None
+
+
+def entmax(x, alpha=1.5, dim=-1, n_iter=50, solver=SOLVER_AUTO):
+    """entmax_bisect(X, alpha, dim, n_iter) (entmax.py:134-175); alpha == 1 gives softmax."""
+    if dim not in (-1, x.dim() - 1):
+        return entmax(x.transpose(dim, -1), alpha, -1, n_iter, solver).transpose(dim, -1)
+    return _EntmaxFn.apply(x, float(alpha), int(n_iter), int(solver))
+
+
+def fused_forward(ids, values, table, bilinear_w, query, att_values, alpha, one_head=False, n_iter=50,
+                  solver=SOLVER_AUTO, clamp: Optional[Tuple[float, float]] = (0.001, 1.0), clamp_inplace=True,
+                  ld: Optional[int] = None, nemb: Optional[int] = None, want_tau=False, want_p=False,
+                  want_g=False, want_s=False, err_flag=None):
+    """The fused hot path (armnet.py:82-87 / armnet_1h.py:81-86): returns z [B, K*O, E] and a dict of the optional
+    outputs ('tau' [B,K*O,2], 'p' [B,K*O,F], 'g' [B,K*O,F], 's' [B,K*O,E])."""
+    _need_cuda(ids, values, table, bilinear_w, query, att_values)
+    ids_c = ids.contiguous()
+    values, _ = _values_inplace(values)
+    table = _f32c(table, 'table')
+    W = _f32c(bilinear_w, 'bilinear_w')
+    Q = _f32c(query, 'query')
+    Vv = _f32c(att_values, 'values')
+    B, F = ids_c.shape
+    V = table.shape[0]
+    ld = table.shape[1] if ld is None else ld
+    E = table.shape[1] if nemb is None else nemb
+    if one_head:
+        D, K, O = W.shape[0], 1, Q.shape[0]
+        assert W.shape == (D, E) and Q.shape == (O, D) and Vv.shape == (O, F)
+    else:
+        K, O, D = Q.shape
+        assert W.shape == (K, E, D) and Vv.shape == (K, O, F)
+    R = K * O
+    dev = table.device
+    ws_bytes = lib.armnet_fused_workspace_bytes(F, E, K, O)
+    if ws_bytes == 0:
+        raise _capi.ArmnetError(f'armnet_fused_fwd_f32: unsupported shape F={F} E={E} (F <= 64, E <= 128)')
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+    z = torch.empty(B, R, E, dtype=torch.float32, device=dev)
+    extra = {}
+    if want_tau:
+        extra['tau'] = torch.empty(B, R, 2, dtype=torch.float32, device=dev)
+    if want_p:
+        extra['p'] = torch.empty(B, R, F, dtype=torch.float32, device=dev)
+    if want_g:
+        extra['g'] = torch.empty(B, R, F, dtype=torch.float32, device=dev)
+    if want_s:
+        extra['s'] = torch.empty(B, R, E, dtype=torch.float32, device=dev)
+    lo, hi = clamp if clamp is not None else (0.0, 0.0)
+
+    def ptr(k):
+        return extra[k].data_ptr() if k in extra else None
+
+    rc = lib.armnet_fused_fwd_f32(
+        ids_c.data_ptr(), _ids_arg(ids_c), values.data_ptr(), table.data_ptr(), V, ld, W.data_ptr(), Q.data_ptr(),
+        Vv.data_ptr(), int(one_head), float(alpha), int(solver), int(n_iter), B, F, E, D, K, O,
+        int(clamp is not None), lo, hi, int(clamp_inplace), z.data_ptr(), ptr('tau'), ptr('p'), ptr('g'),
+        ptr('s'), ws.data_ptr(), err_flag.data_ptr() if err_flag is not None else None, _stream())
+    check(rc, 'armnet_fused_fwd_f32')
+    return z, extra

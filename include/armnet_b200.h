@@ -1,0 +1,111 @@
+/*
+ * armnet_b200.h -- C ABI of the B200-native ARM-Net forward hot path (libarmnet_b200.so).
+ *
+ * The reference (nusdbsystem/ARM-Net @ 7aeb3a4) is pure Python/PyTorch; its "FFI" for this path is
+ * the chain of ATen calls made from models/layers.py, models/armnet.py, models/armnet_1h.py and
+ * utils/entmax.py.  Each entry point below names the reference lines it replaces.  A maintainer binds
+ * these with ctypes; armnet_b200/_capi.py is that binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise
+ *   - tensors are dense row-major fp32 (ids: int64, or int32 when ids_i32 != 0)
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *     calls are asynchronous, re-entrant and keep no mutable global state
+ *   - memory is borrowed: nothing is allocated, freed or retained across calls
+ *   - return value: ARMNET_OK or a negative ARMNET_ERR_* code; never throws, never exits.
+ *     armnet_last_error_string() gives the calling thread's last failure text.
+ *   - out-of-range ids (reference: IndexError from nn.Embedding, layers.py:20) do not fault: the row is
+ *     treated as zeros and bit 0 of *err_flag (device int, may be NULL) is set for the host to check.
+ */
+#ifndef ARMNET_B200_H_
+#define ARMNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARMNET_B200_VERSION 100 /* 0.1.0 */
+
+#define ARMNET_OK 0
+#define ARMNET_ERR_NULL (-1)        /* required pointer is NULL */
+#define ARMNET_ERR_SHAPE (-2)       /* non-positive / inconsistent sizes, alpha < 1 */
+#define ARMNET_ERR_UNSUPPORTED (-3) /* no compiled kernel instance or shared-memory budget exceeded */
+#define ARMNET_ERR_CUDA (-4)        /* CUDA runtime / launch error (text in armnet_last_error_string) */
+#define ARMNET_ERR_ALIGN (-5)       /* pointer not aligned for its element type */
+
+/* Threshold solver for the alpha-entmax gates (utils/entmax.py:29-68). */
+#define ARMNET_SOLVER_AUTO 0   /* alpha==1 softmax; 1<alpha<2 Newton; alpha==2 Michelot; alpha>2 bisection */
+#define ARMNET_SOLVER_BISECT 1 /* the reference's algorithm step by step (n_iter halvings, early exit at the
+                                  fp32 fixed point), for parity validation */
+
+int armnet_version(void);
+const char *armnet_last_error_string(void);
+
+/* Device facts the host side sizes its launches with (SM count, opt-in shared memory per block). */
+int armnet_device_info(int *sm_count, int *smem_optin_bytes);
+
+/*
+ * layers.Embedding.forward (models/layers.py:15-21) fused with the value clamp of
+ * ARMNetModel.forward (models/armnet.py:82, models/armnet_1h.py:81):
+ *     v       = clamp ? min(max(values[b,f], clamp_lo), clamp_hi) : values[b,f]
+ *     out[b,f,:] = table[ids[b,f], 0:E] * v              (one fp32 multiply: bit-exact vs the reference)
+ * values is rewritten in place when clamp_inplace != 0 (the reference mutates the caller's tensor).
+ * table is [V, ld] with ld >= E (row pitch in floats; ld == E for the nn.Embedding parameter itself).
+ */
+int armnet_embed_gather_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V,
+                            int64_t ld, int64_t B, int F, int E, float *out, int clamp, float clamp_lo,
+                            float clamp_hi, int clamp_inplace, int *err_flag, void *stream);
+
+/*
+ * EntmaxBisect.forward / entmax_bisect / nn.Softmax(dim=-1) over the last axis
+ * (utils/entmax.py:238-275, :134-175, :29-68; models/armnet.py:12-13).  x, p: [rows, F].
+ */
+int armnet_entmax_f32(const float *x, int64_t rows, int F, float alpha, int solver, int n_iter, float *p,
+                      void *stream);
+
+/* EntmaxBisectFunction.backward (utils/entmax.py:71-80), softmax backward when alpha == 1.
+ * p, dp, dx: [rows, F]. */
+int armnet_entmax_bwd_f32(const float *p, const float *dp, int64_t rows, int F, float alpha, float *dx,
+                          void *stream);
+
+/* Bytes of device scratch armnet_fused_fwd_f32 needs for the given shape (pre-contracted attention
+ * parameters; batch independent). */
+size_t armnet_fused_workspace_bytes(int F, int E, int K, int O);
+
+/*
+ * The fused hot path: value clamp -> embedding lookup -> attention logits -> alpha-entmax gates ->
+ * gates * values -> exponential-neuron interaction.
+ *   multi-head  models/armnet.py:82-87 with SparseAttLayer.forward :26-36      (w_is_linear_layout == 0)
+ *       bilinear_w [K,E,D], query [K,O,D], att_values [K,O,F]
+ *   one-head    models/armnet_1h.py:81-86 with SparseAttention.forward :25-34  (w_is_linear_layout != 0, K == 1)
+ *       bilinear_w is the nn.Linear weight [D,E], query [O,D], att_values [O,F]
+ *
+ *   e[b,f,:]   = table[ids[b,f],:] * clamp(values[b,f])
+ *   g[b,r,f]   = D^-0.5 * sum_x sum_y e[b,f,x] W[k,x,y] Q[k,o,y]          r = k*O + o
+ *   p[b,r,:]   = entmax_alpha(g[b,r,:])            (softmax when alpha == 1)
+ *   out_z[b,r,:] = exp( sum_f p[b,r,f] * att_values[r,f] * e[b,f,:] )     [B, K*O, E], the layout
+ *                  arm_bn consumes (armnet.py:88 'b k o e -> b (k o) e')
+ *
+ * Optional outputs (NULL to skip): out_tau [B,K*O,2] = (threshold tau, sum of unnormalised gates) per row,
+ * which is all a backward pass needs to rebuild p;  out_p [B,K*O,F] gates;  out_g [B,K*O,F] logits;
+ * out_s [B,K*O,E] the pre-exp sums log(out_z) (validation only: uncoalesced stores).
+ * workspace: armnet_fused_workspace_bytes(F,E,K,O) bytes, 16-byte aligned, rewritten by every call.
+ * Launches two kernels on `stream` (parameter pre-contraction, fused forward).
+ */
+int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V,
+                         int64_t ld, const float *bilinear_w, const float *query, const float *att_values,
+                         int w_is_linear_layout, float alpha, int solver, int n_iter, int64_t B, int F,
+                         int E, int D, int K, int O, int clamp, float clamp_lo, float clamp_hi,
+                         int clamp_inplace, float *out_z, float *out_tau, float *out_p, float *out_g,
+                         float *out_s, void *workspace, int *err_flag, void *stream);
+
+/* Number of kernels the last armnet_fused_fwd_f32 call on this thread launched (bench bookkeeping). */
+int armnet_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARMNET_B200_H_ */

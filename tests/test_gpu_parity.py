@@ -1,0 +1,246 @@
+"""Parity of the CUDA path (through the C ABI) against the reference-generated golden fixtures and the oracle.
+Tolerances (SURVEY.md 8d / BASELINE.json north_star):
+  gather e                      bit-exact
+  logits g, sums s, output z    max|a-b| / max|b| <= 1e-5
+  gates p                       abs <= 2e-6   (entries at the support boundary are ill-conditioned)
+"""
+import pytest
+import torch
+
+from conftest import load_golden, norm_rel, GOLDEN_CASES
+
+pytestmark = pytest.mark.gpu
+
+TOL_NORM = 1e-5
+TOL_P = 2e-6
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def hot_params(g):
+    st = g.state
+    if g.one_head:
+        return st['attn_layer.bilinear_w.weight'], st['attn_layer.query'], st['attn_layer.values']
+    return st['attn_layer.bilinear_w'], st['attn_layer.query'], st['attn_layer.values']
+
+
+def build_model(g, device):
+    import armnet_b200 as ab
+    c = g.cfg
+    if c['model'] == 'armnet':
+        m = ab.ARMNetModel(c['nfield'], c['nfeat'], c['nemb'], c['nhead'], c['alpha'], c['nhid'], c['mlp_nlayer'],
+                           c['mlp_nhid'], 0.0, bool(c['ensemble']), 2, 16)
+    else:
+        m = ab.ARMNet1H(c['nfield'], c['nfeat'], c['nemb'], c['alpha'], c['nhid'], c['d_k'], c['mlp_nlayer'],
+                        c['mlp_nhid'], 0.0, bool(c['ensemble']), 2, 16)
+    m.load_state_dict(g.state)
+    return m.to(device)
+
+
+def test_gather_bit_exact(golden):
+    from armnet_b200 import ops
+    d = dev()
+    vals = golden.values.clone().to(d)
+    e = ops.embed_gather(golden.ids.to(d), vals, golden.state['embedding.embedding.weight'].to(d),
+                         clamp=(0.001, 1.0))
+    assert torch.equal(e.cpu(), golden.out['e'])
+    assert torch.equal(vals.cpu(), golden.out['values_after'])      # in-place clamp, armnet.py:82
+    # int32 ids are accepted too
+    e32 = ops.embed_gather(golden.ids.to(d).int(), vals, golden.state['embedding.embedding.weight'].to(d))
+    assert torch.equal(e32.cpu(), golden.out['e'])
+
+
+@pytest.mark.parametrize('solver', ['auto', 'bisect'])
+@pytest.mark.parametrize('padded', [False, True])
+def test_fused_stages_match_reference(golden, solver, padded):
+    from armnet_b200 import ops
+    d = dev()
+    c = golden.cfg
+    W, Q, Vv = (t.to(d) for t in hot_params(golden))
+    table = golden.state['embedding.embedding.weight'].to(d)
+    E = table.shape[1]
+    ld = E
+    if padded:
+        ld = (E + 3) // 4 * 4 + 4
+        tp = torch.zeros(table.shape[0], ld, device=d)
+        tp[:, :E] = table
+        table = tp
+    vals = golden.values.clone().to(d)
+    z, ex = ops.fused_forward(golden.ids.to(d), vals, table, W, Q, Vv, float(c['alpha']),
+                              one_head=golden.one_head, ld=ld, nemb=E,
+                              solver=ops.SOLVER_BISECT if solver == 'bisect' else ops.SOLVER_AUTO,
+                              want_tau=True, want_p=True, want_g=True, want_s=True)
+    torch.cuda.synchronize()
+    assert torch.equal(vals.cpu(), golden.out['values_after'])
+    B = golden.ids.shape[0]
+    ref = {k: golden.out[k].reshape(B, -1, golden.out[k].shape[-1]) for k in ('g', 'p', 's', 'z')}
+    assert z.shape == ref['z'].shape
+    assert norm_rel(ex['g'].cpu(), ref['g']) <= TOL_NORM
+    assert (ex['p'].cpu() - ref['p']).abs().max().item() <= TOL_P
+    assert norm_rel(ex['s'].cpu(), ref['s']) <= TOL_NORM
+    assert norm_rel(z.cpu(), ref['z']) <= TOL_NORM
+    # gates are a distribution; (tau, sum) rebuilds them
+    assert (ex['p'].sum(-1) - 1).abs().max().item() < 1e-5
+    assert torch.isfinite(ex['tau']).all()
+
+
+def test_fused_plain_call_equals_debug_call(golden):
+    """The optional outputs must not change z."""
+    from armnet_b200 import ops
+    d = dev()
+    W, Q, Vv = (t.to(d) for t in hot_params(golden))
+    table = golden.state['embedding.embedding.weight'].to(d)
+    a = float(golden.cfg['alpha'])
+    z0, _ = ops.fused_forward(golden.ids.to(d), golden.values.clone().to(d), table, W, Q, Vv, a,
+                              one_head=golden.one_head)
+    z1, _ = ops.fused_forward(golden.ids.to(d), golden.values.clone().to(d), table, W, Q, Vv, a,
+                              one_head=golden.one_head, want_p=True, want_g=True, want_s=True, want_tau=True)
+    assert torch.equal(z0, z1)
+
+
+def test_module_forward_matches_reference(golden):
+    d = dev()
+    m = build_model(golden, d).eval()
+    for padded in (True, False):
+        m.padded_table = padded
+        vals = golden.values.clone().to(d)
+        with torch.no_grad():
+            y = m({'id': golden.ids.to(d), 'value': vals})
+        assert y.shape == golden.out['y'].shape          # 0-dim when B == 1 (armnet.py:101)
+        assert torch.equal(vals.cpu(), golden.out['values_after'])
+        err = (y.cpu() - golden.out['y']).abs().max().item()
+        assert err <= 2e-5 * max(1.0, golden.out['y'].abs().max().item()), err
+
+
+def test_entmax_op_forward_backward(golden):
+    from armnet_b200 import ops
+    from oracle import armnet_oracle as oracle
+    d = dev()
+    a = float(golden.cfg['alpha'])
+    g = golden.out['g'].to(d).requires_grad_(True)
+    for solver in (ops.SOLVER_AUTO, ops.SOLVER_BISECT):
+        p = ops.entmax(g, alpha=a, dim=-1, solver=solver)
+        assert (p.detach().cpu() - golden.out['p']).abs().max().item() <= TOL_P
+    gen = torch.Generator().manual_seed(1)
+    dp = torch.randn(golden.out['p'].shape, generator=gen)
+    p.backward(dp.to(d))
+    if a == 1.:
+        pr = golden.out['p']
+        ref = pr * (dp - (dp * pr).sum(-1, keepdim=True))
+    else:
+        ref = oracle.entmax_backward(golden.out['p'], dp, a)
+    assert norm_rel(g.grad.cpu(), ref) <= 2e-5
+
+
+def test_train_step_matches_reference_autograd(golden):
+    if 'y_train' not in golden.out:
+        pytest.skip('fixture has no train-mode pass')
+    d = dev()
+    m = build_model(golden, d).train()
+    y = m({'id': golden.ids.to(d), 'value': golden.values.clone().to(d)})
+    loss = torch.nn.BCEWithLogitsLoss(reduction='mean')(y, golden.target.to(d))
+    loss.backward()
+    assert abs(loss.item() - golden.out['loss'].item()) <= 1e-5
+    assert norm_rel(y.detach().cpu(), golden.out['y_train']) <= 5e-5
+    for n, p in m.named_parameters():
+        ref = golden.out['grad/' + n]
+        assert norm_rel(p.grad.cpu(), ref) <= 2e-4, n
+
+
+# ---------------------------------------------------------------- edge cases and full-size properties
+
+def _criteo_state(seed=2025, nfeat=100000, nemb=10, nhid=128, nhead=4, nfield=39):
+    from oracle import armnet_oracle as oracle
+    return oracle.reference_init_state('armnet', nfield, nfeat, nemb, nhead, nhid, mlp_nhid=32, seed=seed)
+
+
+def test_empty_batch_and_ragged_tiles():
+    from armnet_b200 import ops
+    from oracle import armnet_oracle as oracle
+    d = dev()
+    st = _criteo_state(nhid=16)
+    W, Q, Vv = (st[k].to(d) for k in ('attn_layer.bilinear_w', 'attn_layer.query', 'attn_layer.values'))
+    table = st['embedding.embedding.weight'].to(d)
+    z, _ = ops.fused_forward(torch.zeros(0, 39, dtype=torch.int64, device=d), torch.zeros(0, 39, device=d), table,
+                             W, Q, Vv, 1.7)
+    assert z.shape == (0, 64, 10)
+    gen = torch.Generator().manual_seed(3)
+    for B in (1, 2, 7, 149, 300):            # R = 64: tiles hold 8 samples, so these end in ragged tiles
+        ids = torch.randint(0, 100000, (B, 39), generator=gen)
+        vals = torch.rand(B, 39, generator=gen)
+        ref = oracle.hot_path(st, 1.7, ids, vals.clone())
+        z, _ = ops.fused_forward(ids.to(d), vals.to(d), table, W, Q, Vv, 1.7)
+        assert norm_rel(z.cpu(), ref['z']) <= TOL_NORM, B
+
+
+def test_out_of_range_id_raises_index_error():
+    import armnet_b200 as ab
+    d = dev()
+    torch.manual_seed(0)
+    m = ab.ARMNetModel(5, 50, 10, 2, 1.7, 8, 1, 8, 0.0, False, 1, 8).to(d).eval()
+    m.validate_ids = True
+    ids = torch.randint(0, 50, (4, 5), device=d)
+    with torch.no_grad():
+        m({'id': ids, 'value': torch.ones(4, 5, device=d)})
+        ids[2, 3] = 50
+        with pytest.raises(IndexError):
+            m({'id': ids, 'value': torch.ones(4, 5, device=d)})
+        ids[2, 3] = -1
+        with pytest.raises(IndexError):
+            m({'id': ids, 'value': torch.ones(4, 5, device=d)})
+
+
+def test_bad_arguments_fail_loudly():
+    from armnet_b200 import ops
+    d = dev()
+    t = torch.zeros(10, 10, device=d)
+    with pytest.raises(RuntimeError):        # CPU tensor: no fallback
+        ops.embed_gather(torch.zeros(2, 3, dtype=torch.int64), torch.ones(2, 3), torch.zeros(10, 10))
+    with pytest.raises(TypeError):           # non-contiguous values cannot be clamped in place
+        ops.embed_gather(torch.zeros(2, 3, dtype=torch.int64, device=d), torch.ones(3, 2, device=d).t(), t)
+    with pytest.raises(RuntimeError):        # alpha < 1 -> ARMNET_ERR_SHAPE
+        ops.entmax_forward(torch.zeros(4, 8, device=d), 0.5)
+    with pytest.raises(RuntimeError):        # 65 fields -> ARMNET_ERR_UNSUPPORTED
+        ops.entmax_forward(torch.zeros(4, 65, device=d), 1.5)
+
+
+@pytest.mark.parametrize('regime', ['init', 'trained'])
+def test_full_size_criteo_batch_properties(regime):
+    """BASELINE config 2 at full size (B=4096, 39 fields, 1M vocab, nemb 10, 4 heads x 128 neurons):
+    oracle on a sample of rows, plus size-independent properties on the whole batch."""
+    from armnet_b200 import ops
+    from oracle import armnet_oracle as oracle
+    d = dev()
+    st = _criteo_state(nfeat=1000000)
+    gen = torch.Generator().manual_seed(11)
+    if regime == 'trained':
+        st['embedding.embedding.weight'].normal_(0, 1.0, generator=gen)
+        st['attn_layer.bilinear_w'] *= 4
+        st['attn_layer.query'] *= 4
+    B = 4096
+    ids = torch.randint(0, 1000000, (B, 39), generator=gen)
+    vals = torch.rand(B, 39, generator=gen) * 1.2
+    W, Q, Vv = (st[k].to(d) for k in ('attn_layer.bilinear_w', 'attn_layer.query', 'attn_layer.values'))
+    table = st['embedding.embedding.weight'].to(d)
+    v_d = vals.clone().to(d)
+    z, ex = ops.fused_forward(ids.to(d), v_d, table, W, Q, Vv, 1.7, want_tau=True)
+    assert torch.isfinite(z).all() and (z > 0).all()
+    assert torch.equal(v_d.cpu(), vals.clamp(0.001, 1.0))
+    # oracle on 48 samples spread over the batch
+    pick = torch.arange(0, B, B // 48)[:48]
+    ref = oracle.hot_path(st, 1.7, ids[pick], vals[pick].clone())
+    assert norm_rel(z[pick.to(d)].cpu(), ref['z']) <= TOL_NORM
+    # permutation equivariance over samples (each row only depends on its own sample)
+    perm = torch.randperm(B, generator=gen)
+    z2, _ = ops.fused_forward(ids[perm].to(d), vals[perm].clone().to(d), table, W, Q, Vv, 1.7)
+    assert norm_rel(z2.cpu(), z[perm.to(d)].cpu()) <= 2e-6
+    # determinism
+    z3, _ = ops.fused_forward(ids.to(d), vals.clone().to(d), table, W, Q, Vv, 1.7)
+    assert torch.equal(z3, z)
+    # the padded (TMA-gather) table gives the same bits as the 40-byte-row table
+    tp = torch.zeros(table.shape[0], 12, device=d)
+    tp[:, :10] = table
+    z4, _ = ops.fused_forward(ids.to(d), vals.clone().to(d), tp, W, Q, Vv, 1.7, ld=12, nemb=10)
+    assert torch.equal(z4, z)

@@ -1,0 +1,99 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/armnet_b200.h declares (no compute
+calls without a GPU), argument validation returns error codes instead of crashing, and the drop-in modules keep
+the reference's constructor / state_dict / init-order surface."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    from armnet_b200 import _capi
+    hdr = open(os.path.join(ROOT, 'include', 'armnet_b200.h')).read()
+    body = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(armnet_[a-z0-9_]+)\s*\(', body))
+    assert declared, 'no declarations parsed'
+    raw = ctypes.CDLL(_capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f'{name} declared in the header but not exported'
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    assert _capi.version() == 100
+
+
+def test_argument_validation_without_gpu():
+    from armnet_b200 import _capi
+    lib = _capi.lib
+    assert lib.armnet_fused_workspace_bytes(39, 10, 4, 128) == (12 * 512 + 39 * 512) * 4
+    assert lib.armnet_fused_workspace_bytes(39, 100, 1, 32) > 0
+    assert lib.armnet_fused_workspace_bytes(65, 10, 4, 128) == 0        # > 64 fields: no instance
+    assert lib.armnet_fused_workspace_bytes(39, 129, 4, 128) == 0
+    rc = lib.armnet_entmax_f32(None, 4, 8, 1.5, 0, 50, None, None)
+    assert rc == -1 and b'null' in lib.armnet_last_error_string()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.armnet_entmax_f32(p, 4, 0, 1.5, 0, 50, p, None) == -2   # F == 0
+    assert lib.armnet_entmax_f32(p, 4, 8, 0.5, 0, 50, p, None) == -2   # alpha < 1
+    assert lib.armnet_entmax_f32(p, 4, 65, 1.5, 0, 50, p, None) == -3  # too many fields
+    assert lib.armnet_embed_gather_f32(p, 0, p, p, 10, 4, 2, 3, 8, p, 0, 0.0, 0.0, 0, None, None) == -2  # ld < E
+
+
+def test_ops_refuse_cpu_tensors():
+    from armnet_b200 import ops
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.entmax(torch.zeros(2, 4), 1.5)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.fused_forward(torch.zeros(2, 3, dtype=torch.int64), torch.ones(2, 3), torch.zeros(5, 4),
+                          torch.zeros(1, 4, 4), torch.zeros(1, 2, 4), torch.zeros(1, 2, 3), 1.5)
+
+
+@pytest.mark.parametrize('name', ['c1_1h_frappe', 'c2a_init'])
+def test_same_seed_gives_reference_parameters(name):
+    """Same constructor order and init calls as armnet.py:62-75 / armnet_1h.py:60-74: seeding like train.py:144
+    reproduces the reference's state_dict bit for bit."""
+    import armnet_b200 as ab
+    g = load_golden(name)
+    c = g.cfg
+    torch.manual_seed(2025)
+    if c['model'] == 'armnet':
+        m = ab.ARMNetModel(c['nfield'], c['nfeat'], c['nemb'], c['nhead'], c['alpha'], c['nhid'], c['mlp_nlayer'],
+                           c['mlp_nhid'], 0.0, bool(c['ensemble']), 2, 16)
+    else:
+        m = ab.ARMNet1H(c['nfield'], c['nfeat'], c['nemb'], c['alpha'], c['nhid'], c['d_k'], c['mlp_nlayer'],
+                        c['mlp_nhid'], 0.0, bool(c['ensemble']), 2, 16)
+    sd = m.state_dict()
+    assert set(sd) == set(g.state)
+    for k in sd:
+        assert torch.equal(sd[k], g.state[k]), k
+
+
+def test_state_dict_round_trip_all_fixtures(golden):
+    import armnet_b200 as ab
+    c = golden.cfg
+    if c['model'] == 'armnet':
+        m = ab.ARMNetModel(c['nfield'], c['nfeat'], c['nemb'], c['nhead'], c['alpha'], c['nhid'], c['mlp_nlayer'],
+                           c['mlp_nhid'], 0.0, bool(c['ensemble']), 2, 16)
+    else:
+        m = ab.ARMNet1H(c['nfield'], c['nfeat'], c['nemb'], c['alpha'], c['nhid'], c['d_k'], c['mlp_nlayer'],
+                        c['mlp_nhid'], 0.0, bool(c['ensemble']), 2, 16)
+    m.load_state_dict(golden.state)             # strict: names and shapes are the reference's
+    with pytest.raises(RuntimeError, match='CUDA only'):
+        m({'id': golden.ids, 'value': golden.values.clone()})
+
+
+def test_create_model_surface():
+    import argparse
+    import logging
+    import armnet_b200 as ab
+    args = argparse.Namespace(model='armnet', nfield=10, nfeat=100, nemb=10, nattn_head=4, alpha=1.7, h=8,
+                              mlp_nlayer=2, mlp_nhid=16, dropout=0.0, ensemble=False, dnn_nlayer=2, dnn_nhid=16)
+    m = ab.create_model(args, logging.getLogger('t'))
+    assert isinstance(m, ab.ARMNetModel) and m.attn_layer.values.shape == (4, 8, 10)
+    args.model = 'armnet_1h'
+    assert isinstance(ab.create_model(args, logging.getLogger('t')), ab.ARMNet1H)
+    args.model = 'nope'
+    with pytest.raises(ValueError, match='unknown model'):
+        ab.create_model(args, logging.getLogger('t'))
