@@ -104,6 +104,10 @@ static int launch_fwd(const float *x, long long rows, int F, const EntmaxParams 
 extern "C" int armnet_entmax_f32(const float *x, int64_t rows, int F, float alpha, int solver, int n_iter, float *p,
                                  void *stream) {
     using namespace armnet;
+    if (rows == 0 && F > 0) {
+        note_launches(0);
+        return ARMNET_OK;
+    }
     if (!x || !p) {
         set_error("entmax: null pointer");
         return ARMNET_ERR_NULL;
@@ -144,6 +148,10 @@ extern "C" int armnet_entmax_f32(const float *x, int64_t rows, int F, float alph
 extern "C" int armnet_entmax_bwd_f32(const float *p, const float *dp, int64_t rows, int F, float alpha, float *dx,
                                      void *stream) {
     using namespace armnet;
+    if (rows == 0 && F > 0) {
+        note_launches(0);
+        return ARMNET_OK;
+    }
     if (!p || !dp || !dx) {
         set_error("entmax_bwd: null pointer");
         return ARMNET_ERR_NULL;

@@ -89,6 +89,7 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
                                     float *out_s, void *workspace, int *err_flag, void *stream) {
     using namespace armnet;
     note_launches(0);
+    if (B == 0) return ARMNET_OK;  // empty batch: nothing to read or write (tensors may have null data pointers)
     if (!ids || !values || !table || !bilinear_w || !query || !att_values || !out_z || !workspace) {
         set_error("fused_fwd: null pointer");
         return ARMNET_ERR_NULL;
@@ -112,7 +113,6 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     FwdParams P;
     int rc = make_entmax_params(alpha, F, solver, n_iter, &P.ep);
     if (rc != ARMNET_OK) return rc;
-    if (B == 0) return ARMNET_OK;
     DeviceInfo di;
     rc = get_device_info(&di);
     if (rc != ARMNET_OK) return rc;

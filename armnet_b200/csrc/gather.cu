@@ -59,6 +59,10 @@ extern "C" int armnet_embed_gather_f32(const void *ids, int ids_i32, float *valu
                                        int64_t ld, int64_t B, int F, int E, float *out, int clamp, float clamp_lo,
                                        float clamp_hi, int clamp_inplace, int *err_flag, void *stream) {
     using namespace armnet;
+    if (B == 0) {
+        note_launches(0);
+        return ARMNET_OK;
+    }
     if (!ids || !values || !table || !out) {
         set_error("embed_gather: null pointer");
         return ARMNET_ERR_NULL;

@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the ARM-Net forward hot path (BASELINE.json metric: CTR samples/sec, bsz=4096, Criteo shape).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on the host CPU cores
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N   (one rank per GPU)
+
+One "step" = one pass of the hot path (value clamp -> embedding lookup -> attention logits -> entmax gates ->
+exponential-neuron interaction, armnet.py:82-87) over one synthetic batch of 4096 samples per GPU.
+  value  : samples/s with inputs resident in HBM; CUDA-event time of the K steps (L2 flushed between steps, the
+           flush is outside the events), max over ranks.
+  e2e    : samples/s through the drop-in nn.Module (ARMNetModel.forward -> y[B]) starting from pinned HOST
+           batches: H2D copy of ids/values, fused kernel, BatchNorm + MLP, D2H read of y, all inside the timed region.
+  roofline: algorithmic HBM bytes of the step / event time, against MEASURED_PEAKS.json (hbm_gbs).
+  cpu_baseline: the oracle port of the reference's ATen op chain (oracle/armnet_oracle.py, torch CPU, all host
+           threads) on a bounded sample of the same workload, rank 0 at N=1 only.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: armnet (multi-head) synthetic Criteo-shape, train.py defaults for the rest
+    'c2a': dict(model='armnet', nfield=39, nfeat=1000000, nemb=10, nhead=4, nhid=128, alpha=1.7, bsz=4096,
+                mlp_nlayer=2, mlp_nhid=256),
+    'c2b': dict(model='armnet', nfield=39, nfeat=1000000, nemb=10, nhead=4, nhid=64, alpha=2.0, bsz=4096,
+                mlp_nlayer=2, mlp_nhid=500),
+    'c3': dict(model='armnet', nfield=22, nfeat=1500000, nemb=100, nhead=1, nhid=32, alpha=1.5, bsz=8192,
+               mlp_nlayer=3, mlp_nhid=200),
+    'c4': dict(model='armnet', nfield=39, nfeat=1000000, nemb=16, nhead=4, nhid=128, alpha=1.7, bsz=4096,
+               mlp_nlayer=2, mlp_nhid=256),
+    'c1': dict(model='armnet_1h', nfield=10, nfeat=5382, nemb=10, nhead=1, nhid=10, alpha=1.7, bsz=4096,
+               mlp_nlayer=2, mlp_nhid=256),
+}
+METRIC = 'CTR samples/sec (bsz=4096, Criteo-shape) at 1/2/4/8 B200; HBM GB/s vs roofline'
+
+
+def algorithmic_bytes_per_sample(w):
+    """ids + values + gathered rows + interaction output z."""
+    F, E, R = w['nfield'], w['nemb'], w['nhead'] * w['nhid']
+    return F * (8 + 4 + 4 * E) + 4 * R * E
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == 'Active'})
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def make_batches(w, n, seed, regime_values='ones'):
+    import torch
+    gen = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        ids = torch.randint(0, w['nfeat'], (w['bsz'], w['nfield']), generator=gen, dtype=torch.int64)
+        vals = torch.ones(w['bsz'], w['nfield']) if regime_values == 'ones' else \
+            torch.rand(w['bsz'], w['nfield'], generator=gen)
+        out.append((ids, vals))
+    return out
+
+
+def build_module(w, seed=2025):
+    import torch
+    import armnet_b200 as ab
+    torch.manual_seed(seed)                       # train.py:47,144
+    if w['model'] == 'armnet':
+        return ab.ARMNetModel(w['nfield'], w['nfeat'], w['nemb'], w['nhead'], w['alpha'], w['nhid'],
+                              w['mlp_nlayer'], w['mlp_nhid'], 0.0, False, 2, 256)
+    return ab.ARMNet1H(w['nfield'], w['nfeat'], w['nemb'], w['alpha'], w['nhid'], w['nemb'], w['mlp_nlayer'],
+                       w['mlp_nhid'], 0.0, False, 2, 256)
+
+
+def trained_like_(model, seed=7):
+    """Secondary regime: embedding ~ N(0,1), attention weights x4 -> |logits| O(1..10), gates genuinely sparse."""
+    import torch
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        w = model.embedding.embedding.weight
+        w.copy_(torch.randn(w.shape, generator=gen))
+        a = model.attn_layer
+        (a.bilinear_w if isinstance(a.bilinear_w, torch.nn.Parameter) else a.bilinear_w.weight).mul_(4.0)
+        a.query.mul_(4.0)
+
+
+def cpu_reference_rate(w, state, steps, warmup, sample_b, full_model, seed=99):
+    """The reference algorithm on the host cores: oracle port of the ATen op chain, all threads."""
+    import torch
+    from oracle import armnet_oracle as oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ws = dict(w, bsz=sample_b)
+    batches = make_batches(ws, 2, seed)
+    fn = oracle.forward if full_model else oracle.hot_path
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            ids, vals = batches[i % 2]
+            t0 = time.perf_counter()
+            fn(state, w['alpha'], ids, vals.clone())
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return sample_b * len(times) / total, total / len(times), cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2a', choices=sorted(WORKLOADS))
+    ap.add_argument('--cpu-sample', type=int, default=256, help='samples per CPU-baseline step')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-flush', action='store_true', help='do not flush L2 between timed steps')
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    cfg = {'workload': f"{args.workload}: {w['model']} forward hot path, {w['nfield']} fields, {w['nfeat']} vocab, "
+                       f"nemb={w['nemb']}, nattn_head={w['nhead']}, h={w['nhid']}, alpha={w['alpha']}, "
+                       f"bsz={w['bsz']}/GPU", 'ids': 'uniform[0,V) int64', 'values': 'all 1.0',
+           'params': 'reference init, seed 2025', 'parallelism': f'dp{max(world, args.gpus)} batch-sharded, no collective'}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        import torch
+        from oracle import armnet_oracle as oracle
+        st = oracle.reference_init_state(w['model'], w['nfield'], w['nfeat'], w['nemb'], w['nhead'], w['nhid'],
+                                         mlp_nlayer=w['mlp_nlayer'], mlp_nhid=w['mlp_nhid'], seed=2025)
+        steps = min(args.steps, 8)
+        warm = min(args.warmup, 1)
+        rate, sec, cores = cpu_reference_rate(w, st, steps, warm, args.cpu_sample, full_model=True)
+        sample = (f'{steps} steps x {args.cpu_sample} samples of the same workload (full ARMNetModel.forward, eval), '
+                  f'torch {torch.__version__} CPU, {cores} threads')
+        print(json.dumps({
+            'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'samples/s', 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': warm, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+            'cpu_baseline': {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': rate, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}))
+        return
+
+    # ------------------------------------------------------------------ this repo's CUDA arm
+    import torch
+    import torch.distributed as dist
+    from armnet_b200 import ops
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model = build_module(w).to(dev).eval()
+    n_batches = 4
+    host = [(i.pin_memory(), v.pin_memory()) for i, v in make_batches(w, n_batches, seed=1000 + rank)]
+    resident = [(i.to(dev), v.to(dev)) for i, v in host]
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    table = model.embedding.embedding.weight
+    tab, ld = model._shadow.get(table) if model.padded_table else (table.detach(), table.shape[1])
+    W, Q, Vv = (t.detach() for t in model._attn_weights())
+
+    def hot_step(i):
+        ids, vals = resident[i % n_batches]
+        z, _ = ops.fused_forward(ids, vals, tab, W, Q, Vv, w['alpha'], one_head=model.one_head, ld=ld,
+                                 nemb=table.shape[1])
+        return z
+
+    def timed_hot(steps, warmup):
+        for i in range(warmup):
+            hot_step(i)
+        launches = 0
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for i in range(steps):
+            if flush is not None:
+                flush.zero_()
+            ev[i][0].record()
+            hot_step(i)
+            ev[i][1].record()
+            launches += ops.last_launch_count()
+        barrier()
+        ms = [a.elapsed_time(b) for a, b in ev]
+        return sum(ms), ms, launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms, per_step, launches = timed_hot(args.steps, max(args.warmup, 3))
+
+    # secondary regime (same shapes, trained-like weights: sparse gates, more solver passes)
+    # end to end through the module, host batches
+    def e2e_step(i):
+        ids_h, vals_h = host[i % n_batches]
+        x = {'id': ids_h.to(dev, non_blocking=True), 'value': vals_h.to(dev, non_blocking=True)}
+        with torch.no_grad():
+            y = model(x)
+        return y.cpu()
+
+    for i in range(max(args.warmup, 3)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    trained_like_(model)
+    tab, ld = model._shadow.get(table) if model.padded_table else (table.detach(), table.shape[1])
+    W, Q, Vv = (t.detach() for t in model._attn_weights())
+    tl_ms, _, _ = timed_hot(max(args.steps // 2, 5), 3)
+    tl_steps = max(args.steps // 2, 5)
+
+    t = torch.tensor([total_ms, e2e_s, tl_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s, tl_ms = t.tolist()
+    n = world
+    samples = w['bsz'] * args.steps * n
+    value = samples / (total_ms * 1e-3)
+    ms_per_step = total_ms / args.steps
+    peak, peak_src = peaks()
+    abytes = algorithmic_bytes_per_sample(w) * w['bsz']
+    achieved = abytes / (ms_per_step * 1e-3) / 1e9        # per GPU: one launch processes one batch
+    out = {
+        'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': n, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': dict(cfg, l2='flushed between timed steps (256 MiB memset outside the events)'
+                       if flush is not None else 'not flushed'),
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': abytes,
+                     'kernel': 'armnet_fwd_kernel (+ attn_prepare_kernel, ~1% of the step)',
+                     'note': 'path is FP32-issue/MUFU bound (entmax), not HBM bound; see DESIGN.md'},
+        'e2e': {'value': w['bsz'] * args.steps * n / e2e_s, 'unit': 'samples/s',
+                'h2d_bytes_per_step': w['bsz'] * w['nfield'] * 12, 'd2h_bytes_per_step': w['bsz'] * 4,
+                'ms_per_step': e2e_s / args.steps * 1e3,
+                'what': 'ARMNetModel.forward from pinned host batches: H2D ids+values, fused kernel, BN+MLP, D2H y'},
+        'gpu_launches': launches,
+        'trained_like': {'value': w['bsz'] * tl_steps * n / (tl_ms * 1e-3), 'unit': 'samples/s',
+                         'what': 'same shapes, embedding~N(0,1), attention weights x4 (sparse gates)'},
+        'step_ms_min_med_max': [min(per_step), statistics.median(per_step), max(per_step)],
+        'clocks': clocks,
+    }
+    if rank == 0:
+        if n == 1 and not args.no_cpu_baseline:
+            st = {k: v.detach().cpu() for k, v in build_module(w).state_dict().items()}
+            rate, sec, cores = cpu_reference_rate(w, st, 3, 1, args.cpu_sample, full_model=False)
+            out['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                                   'sample': f'3 steps x {args.cpu_sample} samples of the same workload (hot path '
+                                             f'only), oracle port on torch CPU, {cores} threads, {sec:.2f} s/step'}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

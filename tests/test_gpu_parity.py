@@ -144,9 +144,13 @@ def test_train_step_matches_reference_autograd(golden):
     loss.backward()
     assert abs(loss.item() - golden.out['loss'].item()) <= 1e-5
     assert norm_rel(y.detach().cpu(), golden.out['y_train']) <= 5e-5
+    gmax = max(golden.out['grad/' + n].abs().max().item() for n, _ in m.named_parameters())
     for n, p in m.named_parameters():
         ref = golden.out['grad/' + n]
-        assert norm_rel(p.grad.cpu(), ref) <= 2e-4, n
+        # floor relative to the largest gradient: biases that feed a train-mode BatchNorm have a true gradient of 0
+        # and hold only fp32 noise (1e-9..1e-7) in both implementations
+        err = (p.grad.cpu() - ref).abs().max().item()
+        assert err <= 2e-4 * ref.abs().max().item() + 1e-5 * gmax, (n, err)
 
 
 # ---------------------------------------------------------------- edge cases and full-size properties
