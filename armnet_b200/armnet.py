@@ -79,16 +79,29 @@ class ARMNetModel(nn.Module):
         self.padded_table = True     # keep a 16-byte-aligned shadow table for TMA row gathers in no-grad mode
         self.validate_ids = False    # synchronising id-range check after each forward (reference: IndexError)
         self.solver = ops.SOLVER_AUTO
+        self.fuse_bn = True          # eval mode: apply arm_bn in the kernel epilogue
         self._shadow = _PaddedTable()
         self._err_flag = None
+        self._bn_key = None
 
     # ------------------------------------------------------------------ hot path
     def _attn_weights(self):
         a = self.attn_layer
         return a.bilinear_w, a.query, a.values
 
-    def interaction(self, x, **want):
-        """Fused hot path (armnet.py:82-87): returns z [B, K*O, E] (+ optional stage outputs)."""
+    def _folded_bn(self):
+        """Eval-mode arm_bn (armnet.py:67,89) as the kernel's epilogue: (mean, weight/sqrt(var+eps), bias)."""
+        bn = self.arm_bn
+        key = (bn.weight._version, bn.running_var._version, bn.weight.data_ptr(), bn.running_var.data_ptr())
+        if self._bn_key != key:
+            with torch.no_grad():
+                self._bn_scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            self._bn_key = key
+        return bn.running_mean, self._bn_scale, bn.bias.detach()
+
+    def interaction(self, x, fold_bn=False, **want):
+        """Fused hot path (armnet.py:82-87): returns z [B, K*O, E] (+ optional stage outputs). With fold_bn the
+        eval-mode arm_bn (armnet.py:89) is applied in the kernel epilogue and the result is arm_bn(z)."""
         table = self.embedding.embedding.weight
         if self.padded_table:
             tab, ld = self._shadow.get(table)
@@ -99,7 +112,8 @@ class ARMNetModel(nn.Module):
             self._err_flag = ops.new_error_flag(table.device)
         z, extra = ops.fused_forward(x['id'], x['value'], tab, W.detach(), Q.detach(), Vv.detach(), self.alpha,
                                      one_head=self.one_head, solver=self.solver, ld=ld, nemb=table.shape[1],
-                                     err_flag=self._err_flag if self.validate_ids else None, **want)
+                                     err_flag=self._err_flag if self.validate_ids else None,
+                                     post=self._folded_bn() if fold_bn else None, **want)
         if self.validate_ids:
             ops.raise_if_bad_ids(self._err_flag)
         return (z, extra) if want else z
@@ -121,9 +135,14 @@ class ARMNetModel(nn.Module):
         if not x['value'].is_cuda:
             raise RuntimeError('armnet_b200.ARMNetModel runs on CUDA only (no CPU fallback): move the model and the '
                                'batch to a B200')
-        z = self._interaction_autograd(x) if self._needs_grad() else self.interaction(x)
-        B = z.shape[0]
-        x_arm = self.arm_bn(z).reshape(B, -1)
+        if self._needs_grad():
+            x_arm = self.arm_bn(self._interaction_autograd(x))
+        elif self.arm_bn.training or not self.arm_bn.track_running_stats or not self.fuse_bn:
+            x_arm = self.arm_bn(self.interaction(x))
+        else:
+            x_arm = self.interaction(x, fold_bn=True)     # eval: BatchNorm is a per-neuron affine, fused
+        B = x_arm.shape[0]
+        x_arm = x_arm.reshape(B, -1)
         y = self.mlp(x_arm)
         if hasattr(self, 'ensemble_layer'):
             x_deep = self.deep_embedding(x).reshape(B, -1)

@@ -56,8 +56,10 @@ class ARMNetModel(_MultiHead):
         self.padded_table = True
         self.validate_ids = False
         self.solver = ops.SOLVER_AUTO
+        self.fuse_bn = True
         self._shadow = _PaddedTable()
         self._err_flag = None
+        self._bn_key = None
 
     def _attn_weights(self):
         a = self.attn_layer

@@ -26,22 +26,23 @@ __global__ void __launch_bounds__(kRowsPerCta) entmax_fwd_kernel(const float *__
         __syncthreads();
         const bool valid = tid < nr;
         const float *mine = tile + (valid ? tid : 0) * Fs;
-        float X[FP];
+        float X[1][FP];
 #pragma unroll
-        for (int f = 0; f < FP; ++f) X[f] = (f < F) ? mine[f] * ep.am1 : neg_inf();  // entmax.py:42
-        const float tau = entmax_solve_tau<FP, false>(X, F, ep);
+        for (int f = 0; f < FP; ++f) X[0][f] = (f < F) ? mine[f] * ep.am1 : neg_inf();  // entmax.py:42
+        float tau[1];
+        entmax_solve_tau<1, FP, false>(X, F, ep, tau);
         float s = 0.f;
 #pragma unroll
         for (int f = 0; f < FP; ++f) {
-            X[f] = gate_unnorm_rt(X[f], tau, ep);
-            s += X[f];
+            X[0][f] = gate_unnorm_rt(X[0][f], tau[0], ep);
+            s += X[0][f];
         }
         __syncthreads();  // every thread has read its (or row 0's) logits before any row is overwritten
         if (valid) {
             float *dst = tile + tid * Fs;
 #pragma unroll
             for (int f = 0; f < FP; ++f)
-                if (f < F) dst[f] = __fdiv_rn(X[f], s);  // entmax.py:63-64
+                if (f < F) dst[f] = __fdiv_rn(X[0][f], s);  // entmax.py:63-64
         }
         __syncthreads();
         float *out = p + row0 * F;

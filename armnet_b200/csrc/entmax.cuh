@@ -47,95 +47,147 @@ __device__ __forceinline__ float gate_unnorm_rt(float x, float tau, const Entmax
     }
 }
 
-// X[f] = (alpha-1) * g[f] for f < F (g itself for softmax), -inf for padded f >= F.
+// X[n][f] = (alpha-1) * g[f] of row n for f < F (g itself for softmax), -inf for padded f >= F.
+// NR rows are solved together in one loop (their element-wise work interleaves: twice the ILP per thread); a row that
+// has converged keeps taking Newton steps until every row of every lane has, which only tightens it.
 // All 32 lanes of the warp must call this together (warp-uniform exit votes).
-template <int FP, bool EXACT>
-__device__ __forceinline__ float entmax_solve_tau(const float (&X)[FP], int F, const EntmaxParams &ep) {
-    float mx = X[0];
+template <int NR, int FP, bool EXACT>
+__device__ __forceinline__ void entmax_solve_tau(const float (&X)[NR][FP], int F, const EntmaxParams &ep,
+                                                 float (&tau)[NR]) {
+    float mx[NR];
 #pragma unroll
-    for (int f = 1; f < FP; ++f) mx = fmaxf(mx, X[f]);
-    if (ep.mode == POW_SOFTMAX) return mx;
+    for (int n = 0; n < NR; ++n) {
+        mx[n] = X[n][0];
+#pragma unroll
+        for (int f = 1; f < FP; ++f) mx[n] = fmaxf(mx[n], X[n][f]);
+        tau[n] = mx[n];
+    }
+    if (ep.mode == POW_SOFTMAX) return;
 
     if (ep.mode == POW_BISECT) {
         // entmax.py:46-61, step by step.
-        float tau_lo = mx - 1.f;
-        const float tau_hi = mx - ep.cF;
-        float f_lo = 0.f;
+        float tau_lo[NR], f_lo[NR], dm[NR];
 #pragma unroll
-        for (int f = 0; f < FP; ++f) f_lo += gate_unnorm<POW_BISECT>(X[f], tau_lo, ep);
-        f_lo -= 1.f;
-        float dm = tau_hi - tau_lo;
-        float tau_m = tau_lo;
-        for (int it = 0; it < ep.n_iter; ++it) {
-            dm *= 0.5f;
-            tau_m = tau_lo + dm;
-            // fixed point: every later midpoint equals tau_lo, so every later p_m equals this one
-            const bool fixed = (tau_m == tau_lo);
+        for (int n = 0; n < NR; ++n) {
+            tau_lo[n] = mx[n] - 1.f;
+            const float tau_hi = mx[n] - ep.cF;
             float s = 0.f;
 #pragma unroll
-            for (int f = 0; f < FP; ++f) s += gate_unnorm<POW_BISECT>(X[f], tau_m, ep);
-            const float f_m = s - 1.f;
-            if (f_m * f_lo >= 0.f) tau_lo = tau_m;
+            for (int f = 0; f < FP; ++f) s += gate_unnorm<POW_BISECT>(X[n][f], tau_lo[n], ep);
+            f_lo[n] = s - 1.f;
+            dm[n] = tau_hi - tau_lo[n];
+        }
+        for (int it = 0; it < ep.n_iter; ++it) {
+            bool fixed = true;
+            float s[NR];
+#pragma unroll
+            for (int n = 0; n < NR; ++n) {
+                dm[n] *= 0.5f;
+                tau[n] = tau_lo[n] + dm[n];
+                // fixed point: every later midpoint equals tau_lo, so every later p_m equals this one
+                fixed = fixed && (tau[n] == tau_lo[n]);
+                s[n] = 0.f;
+            }
+#pragma unroll
+            for (int f = 0; f < FP; ++f)
+#pragma unroll
+                for (int n = 0; n < NR; ++n) s[n] += gate_unnorm<POW_BISECT>(X[n][f], tau[n], ep);
+#pragma unroll
+            for (int n = 0; n < NR; ++n)
+                if ((s[n] - 1.f) * f_lo[n] >= 0.f) tau_lo[n] = tau[n];
             if (__all_sync(0xffffffffu, fixed)) break;
         }
-        return tau_m;
+        return;
     }
 
     // Lower bounds on the root: the max element alone gives tau >= max - 1; Jensen on the convex u^q
     // (q >= 1) gives tau >= mean - F^-(1/q) = mean - F^-(alpha-1).
-    float sum = 0.f;
 #pragma unroll
-    for (int f = 0; f < FP; ++f)
-        if (EXACT || f < F) sum += X[f];
-    float tau = fmaxf(mx - 1.f, sum * ep.inv_F - ep.cF);
+    for (int n = 0; n < NR; ++n) {
+        float sum = 0.f;
+#pragma unroll
+        for (int f = 0; f < FP; ++f)
+            if (EXACT || f < F) sum += X[n][f];
+        tau[n] = fmaxf(mx[n] - 1.f, sum * ep.inv_F - ep.cF);
+    }
 
     constexpr int kMaxIt = 12;
     if (ep.mode == POW_GENERAL) {
         const float qm1 = ep.qm1;
         for (int it = 0; it < kMaxIt; ++it) {
-            float s = 0.f, s1 = 0.f;
+            float s[NR], s1[NR];
+#pragma unroll
+            for (int n = 0; n < NR; ++n) s[n] = s1[n] = 0.f;
 #pragma unroll
             for (int f = 0; f < FP; ++f) {
-                const float u = fmaxf(X[f] - tau, 0.f);
-                const float w = fast_ex2(qm1 * fast_lg2(u));  // u^(q-1); u = 0 -> 0 because q-1 > 0
-                s1 += w;
-                s = fmaf(w, u, s);
+#pragma unroll
+                for (int n = 0; n < NR; ++n) {
+                    const float u = fmaxf(X[n][f] - tau[n], 0.f);
+                    const float w = fast_ex2(qm1 * fast_lg2(u));  // u^(q-1); u = 0 -> 0 because q-1 > 0
+                    s1[n] += w;
+                    s[n] = fmaf(w, u, s[n]);
+                }
             }
-            float d = __fdividef(s - 1.f, ep.q * s1);
-            if (!(s1 > 0.f)) d = 0.f;
-            tau += d;  // the step is applied even when it is the last: |f(tau+d)| = O(d^2), and the caller renormalises
-            if (__all_sync(0xffffffffu, fabsf(d) <= 2e-5f)) break;
+            bool done = true;
+#pragma unroll
+            for (int n = 0; n < NR; ++n) {
+                float d = __fdividef(s[n] - 1.f, ep.q * s1[n]);
+                if (!(s1[n] > 0.f)) d = 0.f;
+                // the step is applied even when it is the last: |f(tau+d)| = O(d^2), and the caller renormalises
+                tau[n] += d;
+                done = done && (fabsf(d) <= 2e-5f);
+            }
+            if (__all_sync(0xffffffffu, done)) break;
         }
     } else if (ep.mode == POW_SQUARE) {
         for (int it = 0; it < kMaxIt; ++it) {
-            float s = 0.f, s1 = 0.f;
+            float s[NR], s1[NR];
+#pragma unroll
+            for (int n = 0; n < NR; ++n) s[n] = s1[n] = 0.f;
 #pragma unroll
             for (int f = 0; f < FP; ++f) {
-                const float u = fmaxf(X[f] - tau, 0.f);
-                s1 += u;
-                s = fmaf(u, u, s);
+#pragma unroll
+                for (int n = 0; n < NR; ++n) {
+                    const float u = fmaxf(X[n][f] - tau[n], 0.f);
+                    s1[n] += u;
+                    s[n] = fmaf(u, u, s[n]);
+                }
             }
-            float d = __fdividef(s - 1.f, 2.f * s1);
-            if (!(s1 > 0.f)) d = 0.f;
-            tau += d;
-            if (__all_sync(0xffffffffu, fabsf(d) <= 2e-5f)) break;
+            bool done = true;
+#pragma unroll
+            for (int n = 0; n < NR; ++n) {
+                float d = __fdividef(s[n] - 1.f, 2.f * s1[n]);
+                if (!(s1[n] > 0.f)) d = 0.f;
+                tau[n] += d;
+                done = done && (fabsf(d) <= 2e-5f);
+            }
+            if (__all_sync(0xffffffffu, done)) break;
         }
     } else {  // POW_LINEAR
         for (int it = 0; it < kMaxIt; ++it) {
-            float s = 0.f, cnt = 0.f;
+            float s[NR], cnt[NR];
+#pragma unroll
+            for (int n = 0; n < NR; ++n) s[n] = cnt[n] = 0.f;
 #pragma unroll
             for (int f = 0; f < FP; ++f) {
-                const float u = X[f] - tau;
-                s += fmaxf(u, 0.f);
-                cnt += (u > 0.f) ? 1.f : 0.f;
+#pragma unroll
+                for (int n = 0; n < NR; ++n) {
+                    const float u = X[n][f] - tau[n];
+                    s[n] += fmaxf(u, 0.f);
+                    cnt[n] += (u > 0.f) ? 1.f : 0.f;
+                }
             }
-            float d = __fdividef(s - 1.f, cnt);
-            if (!(cnt > 0.f)) d = 0.f;
-            tau += d;
-            if (__all_sync(0xffffffffu, fabsf(d) <= 2.4e-7f * fmaxf(1.f, fabsf(tau)))) break;
+            bool done = true;
+#pragma unroll
+            for (int n = 0; n < NR; ++n) {
+                float d = __fdividef(s[n] - 1.f, cnt[n]);
+                if (!(cnt[n] > 0.f)) d = 0.f;
+                tau[n] += d;
+                done = done && (fabsf(d) <= 2.4e-7f * fmaxf(1.f, fabsf(tau[n])));
+            }
+            if (__all_sync(0xffffffffu, done)) break;
         }
     }
-    return tau;
 }
 
 }  // namespace armnet

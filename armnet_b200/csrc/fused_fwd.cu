@@ -37,19 +37,25 @@ static const FwdInstance *select_instance(int F, int E) {
     return best;
 }
 
-// M[x][r] = sum_y W[k,x,y] Q[k,o,y] (armnet.py:33: 'bfx,kxy,koy->bkof' contracted over y first; one-head:
-// keys = e W_lin^T then keys.Q, armnet_1h.py:30-31, i.e. W[x,y] = W_lin[y,x]); rows x >= E are zero.
-// Vt[f][r] = att_values[r][f].
+// Pre-contracted attention parameters in the row-pair layout the kernel reads (float2 = rows 2j, 2j+1):
+//   Mg2[j][x] = M'[x][2j..2j+1],  M'[x][r] = (alpha-1) * d_k^-0.5 * sum_y W[k,x,y] Q[k,o,y]   (r = k*O + o)
+//       armnet.py:33-34 'bfx,kxy,koy->bkof' * scale, contracted over y first; entmax.py:42 X = g*(alpha-1).
+//       one-head: keys = e W_lin^T then keys.Q (armnet_1h.py:30-32), i.e. W[x,y] = W_lin[y,x].
+//   Vg2[j][f] = att_values[2j..2j+1][f]                                                      (armnet.py:36)
+// Entries with x >= E, f >= F or row >= R are zero.
 __global__ void attn_prepare_kernel(const float *__restrict__ W, const float *__restrict__ Q,
                                     const float *__restrict__ Vals, int lin_layout, int F, int E, int D, int O, int R,
-                                    int E_pad, float *__restrict__ Mg, float *__restrict__ Vtg) {
-    const int nM = E_pad * R;
-    const int total = nM + F * R;
+                                    int R2, int mstr, int vstr, float scale, float am1, float *__restrict__ Mg2,
+                                    float *__restrict__ Vg2) {
+    const int nM = R2 * mstr * 2;
+    const int total = nM + R2 * vstr * 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         if (i < nM) {
-            const int x = i / R, r = i - x * R;
+            const int half = i & 1, jx = i >> 1;
+            const int j = jx / mstr, x = jx - j * mstr;
+            const int r = 2 * j + half;
             float a = 0.f;
-            if (x < E) {
+            if (x < E && r < R) {
                 const int k = r / O;
                 const float *q = Q + (long long)r * D;
                 if (lin_layout) {
@@ -58,12 +64,15 @@ __global__ void attn_prepare_kernel(const float *__restrict__ W, const float *__
                     const float *w = W + ((long long)k * E + x) * D;
                     for (int y = 0; y < D; ++y) a = fmaf(w[y], q[y], a);
                 }
+                a = (a * scale) * am1;
             }
-            Mg[i] = a;
+            Mg2[i] = a;
         } else {
-            const int j = i - nM;
-            const int f = j / R, r = j - f * R;
-            Vtg[j] = Vals[(long long)r * F + f];
+            const int i2 = i - nM;
+            const int half = i2 & 1, jf = i2 >> 1;
+            const int j = jf / vstr, f = jf - j * vstr;
+            const int r = 2 * j + half;
+            Vg2[i2] = (f < F && r < R) ? Vals[(long long)r * F + f] : 0.f;
         }
     }
 }
@@ -77,15 +86,17 @@ extern "C" size_t armnet_fused_workspace_bytes(int F, int E, int K, int O) {
     if (F <= 0 || E <= 0 || K <= 0 || O <= 0) return 0;
     const FwdInstance *I = select_instance(F, E);
     if (!I) return 0;
-    const size_t R = (size_t)K * O;
-    return ((size_t)I->EC * I->ES * R + (size_t)F * R) * sizeof(float);
+    const size_t R2 = ((size_t)K * O + 1) / 2;
+    const size_t mstr = (size_t)(I->EC * I->ES) | 1, vstr = (size_t)I->FP | 1;
+    return R2 * (mstr + vstr) * 2 * sizeof(float);
 }
 
 extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V,
                                     int64_t ld, const float *bilinear_w, const float *query, const float *att_values,
                                     int w_is_linear_layout, float alpha, int solver, int n_iter, int64_t B, int F,
                                     int E, int D, int K, int O, int clamp, float clamp_lo, float clamp_hi,
-                                    int clamp_inplace, float *out_z, float *out_tau, float *out_p, float *out_g,
+                                    int clamp_inplace, const float *post_mean, const float *post_scale,
+                                    const float *post_shift, float *out_z, float *out_tau, float *out_p, float *out_g,
                                     float *out_s, void *workspace, int *err_flag, void *stream) {
     using namespace armnet;
     note_launches(0);
@@ -118,16 +129,26 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     if (rc != ARMNET_OK) return rc;
 
     const int R = K * O;
-    const int E_pad = I->EC * I->ES;
+    const int R2 = (R + 1) / 2;
     const int ES = I->ES;
-    float *Mg = (float *)workspace;
-    float *Vtg = Mg + (size_t)E_pad * R;
+    const int E_lanes = I->EC * ES;
+    const int E_stride = round_up(E_lanes, 4);
+    const int mstr = E_lanes | 1, vstr = I->FP | 1;
+    float *Mg2 = (float *)workspace;
+    float *Vg2 = Mg2 + (size_t)R2 * mstr * 2;
+    if ((post_scale != nullptr) != (post_mean != nullptr) || (post_scale != nullptr) != (post_shift != nullptr)) {
+        set_error("fused_fwd: post_mean/post_scale/post_shift must be given together");
+        return ARMNET_ERR_NULL;
+    }
 
     P.ids = ids;
     P.values = values;
     P.table = table;
-    P.Mg = Mg;
-    P.Vtg = Vtg;
+    P.Mg2 = (const float2 *)Mg2;
+    P.Vg2 = (const float2 *)Vg2;
+    P.post_mean = post_mean;
+    P.post_scale = post_scale;
+    P.post_shift = post_shift;
     P.out_z = out_z;
     P.out_tau = out_tau;
     P.out_p = out_p;
@@ -140,15 +161,17 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     P.F = F;
     P.E = E;
     P.R = R;
+    P.R2 = R2;
     P.ids_i32 = ids_i32;
     P.clamp = clamp;
     P.clamp_inplace = clamp_inplace;
     P.clamp_lo = clamp_lo;
     P.clamp_hi = clamp_hi;
-    P.scale = (float)pow((double)D, -0.5);  // armnet.py:15 `d_k ** -0.5`, rounded to fp32 at use (:34)
+    const float scale = (float)pow((double)D, -0.5);  // armnet.py:15 `d_k ** -0.5`, rounded to fp32 at use (:34)
+    P.g_unscale = 1.f / P.ep.am1;
 
     // ---- launch geometry: NT consumer threads, TS samples per tile
-    const long long items = (long long)R * ES;  // threads one sample occupies
+    const long long items = (long long)R2 * ES;  // threads one sample occupies (one lane group per row pair)
     int best_nt = 0, best_ts = 1;
     double best_eff = -1.0;
     for (int nt = kMaxConsumerThreads; nt >= 64; nt -= 32) {
@@ -181,13 +204,14 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     // ---- TMA eligibility
     P.row_bytes = round_up(E * 4, 16);
     P.tma_gather = ((ld * 4) % 16 == 0 && (uintptr_t)table % 16 == 0 && P.row_bytes <= ld * 4) ? 1 : 0;
-    const int rpp = P.NT / ES;
-    P.tma_store = (((long long)R * E) % 4 == 0 && ((long long)rpp * E) % 4 == 0 && (uintptr_t)out_z % 16 == 0) ? 1 : 0;
+    const int ppp = P.NT / ES;  // row pairs per pass
+    P.tma_store = (R % 2 == 0 && ((long long)R * E) % 4 == 0 && ((long long)ppp * kNR * E) % 4 == 0 &&
+                   (uintptr_t)out_z % 16 == 0) ? 1 : 0;
 
     // ---- shared-memory budget: drop a pipeline stage, then shrink the tile
     P.n_stages = kMaxStages;
     for (;;) {
-        const SmemLayout L(I->FP, E_pad, ES, P);
+        const SmemLayout L(I->FP, E_lanes, E_stride, ES, P);
         if (L.total <= di.smem_optin) break;
         if (P.n_stages > 2) {
             P.n_stages--;
@@ -199,7 +223,7 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
             return ARMNET_ERR_UNSUPPORTED;
         }
     }
-    const SmemLayout L(I->FP, E_pad, ES, P);
+    const SmemLayout L(I->FP, E_lanes, E_stride, ES, P);
     const long long n_tiles = (B + P.TS - 1) / P.TS;
     if (n_tiles > 0x7fffffffLL) {
         set_error("fused_fwd: batch too large");
@@ -210,11 +234,11 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
 
     cudaStream_t st = (cudaStream_t)stream;
     {
-        const int total = E_pad * R + F * R;
+        const int total = R2 * (mstr + vstr) * 2;
         int blocks = (total + 255) / 256;
         if (blocks > di.sm_count * 4) blocks = di.sm_count * 4;
-        attn_prepare_kernel<<<blocks, 256, 0, st>>>(bilinear_w, query, att_values, w_is_linear_layout, F, E, D, O, R,
-                                                     E_pad, Mg, Vtg);
+        attn_prepare_kernel<<<blocks, 256, 0, st>>>(bilinear_w, query, att_values, w_is_linear_layout, F, E, D, O, R, R2,
+                                                     mstr, vstr, scale, P.ep.am1, Mg2, Vg2);
         ARMNET_CUDA_TRY(cudaGetLastError());
     }
     ARMNET_CUDA_TRY(cudaFuncSetAttribute(I->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));

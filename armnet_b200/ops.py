@@ -133,9 +133,10 @@ def entmax(x, alpha=1.5, dim=-1, n_iter=50, solver=SOLVER_AUTO):
 def fused_forward(ids, values, table, bilinear_w, query, att_values, alpha, one_head=False, n_iter=50,
                   solver=SOLVER_AUTO, clamp: Optional[Tuple[float, float]] = (0.001, 1.0), clamp_inplace=True,
                   ld: Optional[int] = None, nemb: Optional[int] = None, want_tau=False, want_p=False,
-                  want_g=False, want_s=False, err_flag=None):
+                  want_g=False, want_s=False, err_flag=None, post=None):
     """The fused hot path (armnet.py:82-87 / armnet_1h.py:81-86): returns z [B, K*O, E] and a dict of the optional
-    outputs ('tau' [B,K*O,2], 'p' [B,K*O,F], 'g' [B,K*O,F], 's' [B,K*O,E])."""
+    outputs ('tau' [B,K*O,2], 'p' [B,K*O,F], 'g' [B,K*O,F], 's' [B,K*O,E]).
+    post=(mean, scale, shift), each [K*O]: eval-mode arm_bn epilogue z <- (z - mean) * scale + shift (armnet.py:89)."""
     _need_cuda(ids, values, table, bilinear_w, query, att_values)
     ids_c = ids.contiguous()
     values, _ = _values_inplace(values)
@@ -170,6 +171,11 @@ def fused_forward(ids, values, table, bilinear_w, query, att_values, alpha, one_
     if want_s:
         extra['s'] = torch.empty(B, R, E, dtype=torch.float32, device=dev)
     lo, hi = clamp if clamp is not None else (0.0, 0.0)
+    pm = ps = pb = None
+    if post is not None:
+        pm, ps, pb = (_f32c(t, 'post') for t in post)
+        _need_cuda(pm, ps, pb)
+        assert pm.numel() == R and ps.numel() == R and pb.numel() == R
 
     def ptr(k):
         return extra[k].data_ptr() if k in extra else None
@@ -177,7 +183,9 @@ def fused_forward(ids, values, table, bilinear_w, query, att_values, alpha, one_
     rc = lib.armnet_fused_fwd_f32(
         ids_c.data_ptr(), _ids_arg(ids_c), values.data_ptr(), table.data_ptr(), V, ld, W.data_ptr(), Q.data_ptr(),
         Vv.data_ptr(), int(one_head), float(alpha), int(solver), int(n_iter), B, F, E, D, K, O,
-        int(clamp is not None), lo, hi, int(clamp_inplace), z.data_ptr(), ptr('tau'), ptr('p'), ptr('g'),
+        int(clamp is not None), lo, hi, int(clamp_inplace),
+        pm.data_ptr() if post is not None else None, ps.data_ptr() if post is not None else None,
+        pb.data_ptr() if post is not None else None, z.data_ptr(), ptr('tau'), ptr('p'), ptr('g'),
         ptr('s'), ws.data_ptr(), err_flag.data_ptr() if err_flag is not None else None, _stream())
     check(rc, 'armnet_fused_fwd_f32')
     return z, extra

@@ -89,6 +89,10 @@ size_t armnet_fused_workspace_bytes(int F, int E, int K, int O);
  *   out_z[b,r,:] = exp( sum_f p[b,r,f] * att_values[r,f] * e[b,f,:] )     [B, K*O, E], the layout
  *                  arm_bn consumes (armnet.py:88 'b k o e -> b (k o) e')
  *
+ * Optional epilogue (all three NULL to skip): eval-mode arm_bn = BatchNorm1d(K*O) on [B,K*O,E] (armnet.py:67,89),
+ *   out_z[b,r,:] <- (out_z[b,r,:] - post_mean[r]) * post_scale[r] + post_shift[r]
+ * with post_mean = running_mean, post_scale = weight / sqrt(running_var + eps), post_shift = bias   ([K*O] each).
+ *
  * Optional outputs (NULL to skip): out_tau [B,K*O,2] = (threshold tau, sum of unnormalised gates) per row,
  * which is all a backward pass needs to rebuild p;  out_p [B,K*O,F] gates;  out_g [B,K*O,F] logits;
  * out_s [B,K*O,E] the pre-exp sums log(out_z) (validation only: uncoalesced stores).
@@ -99,7 +103,8 @@ int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values, const floa
                          int64_t ld, const float *bilinear_w, const float *query, const float *att_values,
                          int w_is_linear_layout, float alpha, int solver, int n_iter, int64_t B, int F,
                          int E, int D, int K, int O, int clamp, float clamp_lo, float clamp_hi,
-                         int clamp_inplace, float *out_z, float *out_tau, float *out_p, float *out_g,
+                         int clamp_inplace, const float *post_mean, const float *post_scale,
+                         const float *post_shift, float *out_z, float *out_tau, float *out_p, float *out_g,
                          float *out_s, void *workspace, int *err_flag, void *stream);
 
 /* Number of kernels the last armnet_fused_fwd_f32 call on this thread launched (bench bookkeeping). */

@@ -103,8 +103,9 @@ def test_fused_plain_call_equals_debug_call(golden):
 def test_module_forward_matches_reference(golden):
     d = dev()
     m = build_model(golden, d).eval()
-    for padded in (True, False):
+    for padded, fuse_bn in ((True, True), (False, True), (True, False)):
         m.padded_table = padded
+        m.fuse_bn = fuse_bn
         vals = golden.values.clone().to(d)
         with torch.no_grad():
             y = m({'id': golden.ids.to(d), 'value': vals})
@@ -112,6 +113,25 @@ def test_module_forward_matches_reference(golden):
         assert torch.equal(vals.cpu(), golden.out['values_after'])
         err = (y.cpu() - golden.out['y']).abs().max().item()
         assert err <= 2e-5 * max(1.0, golden.out['y'].abs().max().item()), err
+
+
+def test_fused_batchnorm_epilogue(golden):
+    """Eval-mode arm_bn folded into the kernel (armnet.py:89) against the oracle's batch_norm of the reference z."""
+    from armnet_b200 import ops
+    from oracle import armnet_oracle as oracle
+    d = dev()
+    W, Q, Vv = (t.to(d) for t in hot_params(golden))
+    table = golden.state['embedding.embedding.weight'].to(d)
+    st = golden.state
+    scale = st['arm_bn.weight'] * torch.rsqrt(st['arm_bn.running_var'] + 1e-5)
+    post = (st['arm_bn.running_mean'].to(d), scale.to(d), st['arm_bn.bias'].to(d))
+    zb, _ = ops.fused_forward(golden.ids.to(d), golden.values.clone().to(d), table, W, Q, Vv,
+                              float(golden.cfg['alpha']), one_head=golden.one_head, post=post)
+    ref = oracle.batchnorm1d(golden.out['z'], st, 'arm_bn.', training=False)
+    # BN divides z - mean (z ~ 1) by sqrt(var): a 1-ulp difference in z is amplified by scale, so the bound is
+    # relative to scale * |z| rather than to the (possibly tiny) normalised value
+    bound = 2e-6 * (scale.abs().max() * golden.out['z'].abs().max()).item() + 1e-5 * ref.abs().max().item()
+    assert (zb.cpu() - ref).abs().max().item() <= bound
 
 
 def test_entmax_op_forward_backward(golden):

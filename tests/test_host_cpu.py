@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 def test_argument_validation_without_gpu():
     from armnet_b200 import _capi
     lib = _capi.lib
-    assert lib.armnet_fused_workspace_bytes(39, 10, 4, 128) == (12 * 512 + 39 * 512) * 4
+    assert lib.armnet_fused_workspace_bytes(39, 10, 4, 128) == 256 * (11 + 39) * 2 * 4   # row pairs x odd strides
     assert lib.armnet_fused_workspace_bytes(39, 100, 1, 32) > 0
     assert lib.armnet_fused_workspace_bytes(65, 10, 4, 128) == 0        # > 64 fields: no instance
     assert lib.armnet_fused_workspace_bytes(39, 129, 4, 128) == 0
