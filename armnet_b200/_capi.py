@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libarmnet_b200.so')
+LIB_PATH = os.environ.get('ARMNET_B200_LIB') or os.path.join(_HERE, 'libarmnet_b200.so')   # env: tuning builds only
 
 OK = 0
 ERR_NAMES = {-1: 'ARMNET_ERR_NULL', -2: 'ARMNET_ERR_SHAPE', -3: 'ARMNET_ERR_UNSUPPORTED', -4: 'ARMNET_ERR_CUDA',

@@ -1,6 +1,7 @@
 // armnet_fused_fwd_f32: host side of the fused forward (instance selection, launch geometry, parameter
 // pre-contraction).  Kernel: fused_fwd.cuh.  Instances: fused_fwd_inst_*.cu.
 #include <math.h>
+#include <stdlib.h>
 
 #include "fused_fwd.cuh"
 
@@ -88,7 +89,7 @@ extern "C" size_t armnet_fused_workspace_bytes(int F, int E, int K, int O) {
     if (!I) return 0;
     const size_t R2 = ((size_t)K * O + 1) / 2;
     const size_t mstr = (size_t)(I->EC * I->ES) | 1, vstr = (size_t)I->FP | 1;
-    return R2 * (mstr + vstr) * 2 * sizeof(float);
+    return (R2 * mstr * 8 + 15) / 16 * 16 + (R2 * vstr * 8 + 15) / 16 * 16;  // bulk-copy granularity
 }
 
 extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V,
@@ -116,6 +117,10 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
         set_error("fused_fwd: misaligned pointer");
         return ARMNET_ERR_ALIGN;
     }
+    if (V > 0x7fffffffLL) {
+        set_error("fused_fwd: nfeat=%lld exceeds the 2^31-1 rows the kernel indexes", (long long)V);
+        return ARMNET_ERR_UNSUPPORTED;
+    }
     const FwdInstance *I = select_instance(F, E);
     if (!I) {
         set_error("fused_fwd: no compiled kernel instance for F=%d E=%d (F <= 64, E <= 128 in this build)", F, E);
@@ -135,7 +140,7 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     const int E_stride = round_up(E_lanes, 4);
     const int mstr = E_lanes | 1, vstr = I->FP | 1;
     float *Mg2 = (float *)workspace;
-    float *Vg2 = Mg2 + (size_t)R2 * mstr * 2;
+    float *Vg2 = Mg2 + ((size_t)R2 * mstr * 8 + 15) / 16 * 4;  // 16-byte padded M table, then V
     if ((post_scale != nullptr) != (post_mean != nullptr) || (post_scale != nullptr) != (post_shift != nullptr)) {
         set_error("fused_fwd: post_mean/post_scale/post_shift must be given together");
         return ARMNET_ERR_NULL;
@@ -170,67 +175,75 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     const float scale = (float)pow((double)D, -0.5);  // armnet.py:15 `d_k ** -0.5`, rounded to fp32 at use (:34)
     P.g_unscale = 1.f / P.ep.am1;
 
-    // ---- launch geometry: NT consumer threads, TS samples per tile
-    const long long items = (long long)R2 * ES;  // threads one sample occupies (one lane group per row pair)
-    int best_nt = 0, best_ts = 1;
-    double best_eff = -1.0;
-    for (int nt = kMaxConsumerThreads; nt >= 64; nt -= 32) {
-        double eff;
-        int ts;
-        if (items >= nt) {
-            ts = 1;
-            const long long passes = (items + nt - 1) / nt;
-            eff = (double)items / (double)(passes * nt);
-        } else {
-            ts = (int)(nt / items);
-            eff = (double)(ts * items) / nt;
-        }
-        if (eff > best_eff + 1e-9) {
-            best_eff = eff;
-            best_nt = nt;
-            best_ts = ts;
-        }
+    // ---- launch geometry (fused_fwd.cuh): tiles of SPG samples, UPG warp-units per tile, NW warps per CTA
+    const int PPW = 32 / ES;  // row pairs per warp-unit
+    if (R2 >= PPW) {
+        P.SPG = 1;
+        P.UPG = (R2 + PPW - 1) / PPW;
+    } else {
+        P.SPG = PPW / R2;  // several whole samples per unit
+        P.UPG = 1;
+        long long cap = (B + di.sm_count - 1) / di.sm_count;  // keep every SM busy on small batches
+        if (cap < 1) cap = 1;
+        if (P.SPG > cap) P.SPG = (int)cap;
     }
-    long long ts_cap = (B + di.sm_count - 1) / di.sm_count;  // keep every SM busy on small batches
-    if (ts_cap < 1) ts_cap = 1;
-    if (best_ts > ts_cap) {
-        best_ts = (int)ts_cap;
-        const int need = round_up((int)(best_ts * items), 32);
-        if (need < best_nt) best_nt = need < 64 ? 64 : need;
-    }
-    P.NT = best_nt;
-    P.TS = best_ts;
-
-    // ---- TMA eligibility
-    P.row_bytes = round_up(E * 4, 16);
-    P.tma_gather = ((ld * 4) % 16 == 0 && (uintptr_t)table % 16 == 0 && P.row_bytes <= ld * 4) ? 1 : 0;
-    const int ppp = P.NT / ES;  // row pairs per pass
-    P.tma_store = (R % 2 == 0 && ((long long)R * E) % 4 == 0 && ((long long)ppp * kNR * E) % 4 == 0 &&
-                   (uintptr_t)out_z % 16 == 0) ? 1 : 0;
-
-    // ---- shared-memory budget: drop a pipeline stage, then shrink the tile
-    P.n_stages = kMaxStages;
-    for (;;) {
-        const SmemLayout L(I->FP, E_lanes, E_stride, ES, P);
-        if (L.total <= di.smem_optin) break;
-        if (P.n_stages > 2) {
-            P.n_stages--;
-        } else if (P.TS > 1) {
-            P.TS = (P.TS + 1) / 2;
-        } else {
-            set_error("fused_fwd: F=%d E=%d K*O=%d needs %d bytes of shared memory per CTA (limit %d)", F, E, R, L.total,
-                      di.smem_optin);
-            return ARMNET_ERR_UNSUPPORTED;
-        }
-    }
-    const SmemLayout L(I->FP, E_lanes, E_stride, ES, P);
-    const long long n_tiles = (B + P.TS - 1) / P.TS;
-    if (n_tiles > 0x7fffffffLL) {
+    const long long n_tiles = (B + P.SPG - 1) / P.SPG;
+    if (n_tiles > 0x7fffffffLL / P.UPG) {
         set_error("fused_fwd: batch too large");
         return ARMNET_ERR_SHAPE;
     }
     P.n_tiles = (int)n_tiles;
     const unsigned grid = (unsigned)(n_tiles < di.sm_count ? n_tiles : di.sm_count);
+    const long long units_per_cta = (n_tiles + grid - 1) / grid * P.UPG;
+    P.NW = (int)(units_per_cta < kMaxWarps ? units_per_cta : kMaxWarps);
+    if (const char *f = getenv("ARMNET_FORCE_NW")) {  // tuning experiments only
+        const int nw = atoi(f);
+        if (nw >= 1 && nw <= kMaxWarps) P.NW = nw;
+    }
+    P.lockstep = getenv("ARMNET_DYNAMIC") ? 0 : 1;
+    P.dbg_skip = getenv("ARMNET_DEBUG_SKIP") ? atoi(getenv("ARMNET_DEBUG_SKIP")) : 0;
+
+    // ---- TMA eligibility
+    P.row_bytes = round_up(E * 4, 16);
+    P.tma_gather = ((ld * 4) % 16 == 0 && (uintptr_t)table % 16 == 0 && P.row_bytes <= ld * 4) ? 1 : 0;
+    if (getenv("ARMNET_NO_TMA_GATHER")) P.tma_gather = 0;
+    // a unit's output rows are contiguous when pairs never straddle samples (R even); 16-byte size/alignment of each
+    // bulk store is re-checked per unit in the kernel
+    P.tma_store = (getenv("ARMNET_NO_TMA_STORE") == nullptr && R % 2 == 0 && (uintptr_t)out_z % 16 == 0) ? 1 : 0;
+
+    // ---- shared-memory budget: ids/values of an epoch of tiles are preloaded; the rest of the space becomes gather
+    // slots (the deeper the ring, the further ahead the TMA gathers run)
+    const int n_local_max = (int)((n_tiles + grid - 1) / grid);
+    const int in_flight = (P.NW + P.UPG - 1) / P.UPG;  // tiles being consumed at once
+    const int rows_pad = round_up(P.SPG * F, 4);
+    P.TPE = n_local_max;
+    if ((long long)P.TPE * rows_pad * 8 > 32 * 1024) P.TPE = (32 * 1024) / (rows_pad * 8);
+    if (P.TPE < 1) P.TPE = 1;
+    int best_slots = 0;
+    for (int ns = kMaxSlots; ns >= in_flight + 2; --ns) {
+        P.n_slots = ns;
+        const SmemLayout Lt(I->FP, E_lanes, E_stride, ES, P);
+        if (Lt.total <= di.smem_optin) {
+            best_slots = ns;
+            break;
+        }
+    }
+    if (best_slots == 0) {
+        P.n_slots = in_flight + 2;
+        const SmemLayout Lt(I->FP, E_lanes, E_stride, ES, P);
+        set_error("fused_fwd: F=%d E=%d K*O=%d needs %d bytes of shared memory per CTA (limit %d)", F, E, R, Lt.total,
+                  di.smem_optin);
+        return ARMNET_ERR_UNSUPPORTED;
+    }
+    if (best_slots > n_local_max + in_flight + 1) best_slots = n_local_max + in_flight + 1;  // no more than useful
+    if (best_slots < in_flight + 2) best_slots = in_flight + 2;
+    P.n_slots = best_slots;
+    P.look = P.n_slots - in_flight - 1;
+    if (const char *f = getenv("ARMNET_FORCE_LOOK")) {  // tuning experiments only
+        const int lk = atoi(f);
+        if (lk >= 1 && lk <= P.look) P.look = lk;
+    }
+    const SmemLayout L(I->FP, E_lanes, E_stride, ES, P);
 
     cudaStream_t st = (cudaStream_t)stream;
     {
@@ -243,7 +256,7 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     }
     ARMNET_CUDA_TRY(cudaFuncSetAttribute(I->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
     void *args[] = {(void *)&P};
-    ARMNET_CUDA_TRY(cudaLaunchKernel(I->kernel, dim3(grid), dim3(P.NT + kProducerThreads), args, (size_t)L.total, st));
+    ARMNET_CUDA_TRY(cudaLaunchKernel(I->kernel, dim3(grid), dim3(P.NW * 32), args, (size_t)L.total, st));
     note_launches(2);
     return ARMNET_OK;
 }

@@ -4,34 +4,39 @@
 //
 // Shape of the work.  A "row" is one (sample b, exponential neuron r = k*O + o).  A row needs the sample's F gathered
 // embedding vectors e[f, 0:E] (shared by all R rows of the sample), its own column of the pre-contracted attention
-// matrix M[x, r] = (alpha-1) d_k^-0.5 sum_y W[k,x,y] Q[k,o,y], and its own column of the value matrix V[r, f];
-// it produces E outputs.
+// matrix M'[x, r] = (alpha-1) d_k^-0.5 sum_y W[k,x,y] Q[k,o,y], and its own row of the value matrix V[r, f];
+// it produces E outputs.  The kernel is latency-/issue-bound (entmax), not HBM-bound: measured throughput scales
+// linearly with resident warps, so the design maximises warps at a register budget that holds 2 x F logits.
 //
-// Mapping.  Persistent CTAs (one per SM), warp-specialised:
-//   * 1 producer warp: per tile of TS samples it reads ids/values (coalesced), clamps the values (writing them back
-//     in place like the reference), and gathers the TS*F embedding rows into a shared-memory stage -- with TMA bulk
-//     copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) when rows are 16-byte aligned, otherwise with
-//     8-/4-byte loads -- then scales each row by its value so consumers see e = T[id]*v exactly as layers.py:21
-//     computes it.  A 2-3 stage full/empty mbarrier ring decouples it from the consumers.
-//   * NT <= 256 consumer threads.  ES adjacent lanes own one PAIR of adjacent rows (ES = 1 when E <= 16): every e value
-//     read from shared memory (warp-broadcast LDS.128) feeds both rows, M and V come as float2 (one value per row of
-//     the pair) from conflict-free odd-stride tables.  The 2 x F logits live in registers (thread-private, so the
-//     entmax reductions need no shuffles), tau is found by the solvers in entmax.cuh, and the same registers feed the
-//     cross product s[x] = sum_f p_f V_f e[f,x].  9 warps per SM -> 168 registers per thread, no spills.
-//   * output: z rows of one pass are contiguous in global memory ([B, R, E] layout), so they are staged in shared
-//     memory and written with one TMA bulk store per pass (double-buffered), or with direct stores when the
-//     16-byte granularity of bulk copies does not fit the shape.
+// Mapping.  Persistent CTAs (one per SM) of NW symmetric warps; no CTA-wide barrier after start-up.
+//   * tile  = SPG consecutive samples whose F embedding rows sit in one shared-memory slot of a ring (mbarriers
+//     raw/full/empty per slot).  unit = the PPW = 32/ES row pairs one warp processes at a time; a tile has UPG units.
+//     Warps take units in order from a shared counter and walk them independently of each other.
+//   * gather: the warp that takes a tile's first unit (a) scales the rows of that tile, which landed long ago, by
+//     their values so every consumer sees e = T[id]*v exactly as layers.py:21 computes it, and releases the tile on
+//     the full mbarrier; then (b) issues the gather of the tile two ahead -- ids/values are read coalesced, values
+//     clamped (and written back in place like the reference), rows fetched with TMA bulk copies (cp.async.bulk ->
+//     UBLKCP, byte-counted on the slot's raw mbarrier) when they are 16-byte aligned, else with 8-/4-byte loads.
+//   * compute: ES adjacent lanes own one PAIR of adjacent rows (ES = 1 when E <= 16).  Every e value read from shared
+//     memory (warp-broadcast LDS.128) feeds both rows; M' and V come as float2 (one value per row of the pair) from
+//     conflict-free odd-stride tables.  The 2 x F logits live in registers (thread-private: the entmax reductions
+//     need no shuffles), tau comes from the solvers in entmax.cuh, the same registers feed s[x] = sum_f p_f V_f e[f,x].
+//   * output: a unit's z rows are contiguous in global memory ([B, R, E] layout): they are staged in the warp's own
+//     shared-memory buffer and written with one TMA bulk store per unit, or with direct stores when the 16-byte
+//     granularity of bulk copies does not fit the shape.
 #pragma once
 
 #include "entmax.cuh"
 
 namespace armnet {
 
-constexpr int kMaxConsumerThreads = 256;
-constexpr int kProducerThreads = 32;
-constexpr int kMaxThreads = kMaxConsumerThreads + kProducerThreads;
-constexpr int kMaxStages = 3;
-constexpr int kNR = 2;  // rows per thread
+#ifndef ARMNET_MAX_WARPS
+#define ARMNET_MAX_WARPS 12  // 12 warps -> 3 per SM sub-partition -> 168 registers per thread
+#endif
+constexpr int kMaxWarps = ARMNET_MAX_WARPS;
+constexpr int kMaxThreads = kMaxWarps * 32;
+constexpr int kMaxSlots = 24;
+constexpr int kNR = 2;    // rows per thread
 
 struct FwdParams {
     const void *ids;
@@ -55,38 +60,47 @@ struct FwdParams {
     float clamp_lo, clamp_hi;
     float g_unscale;  // 1 / (alpha-1): logits g = X * g_unscale for the validation output
     EntmaxParams ep;
-    int TS;          // samples per tile
-    int NT;          // consumer threads (multiple of 32)
+    int SPG;         // samples per tile
+    int UPG;         // warp-units per tile
+    int NW;          // warps per CTA
+    int n_slots;     // ring size
+    int look;        // tiles of gather look-ahead
+    int TPE;         // tiles per epoch (ids/values of one epoch are preloaded into shared memory)
     int n_tiles;
-    int n_stages;    // 2 or 3
     int tma_gather;  // 1: rows fetched with cp.async.bulk of row_bytes each
     int row_bytes;
-    int tma_store;   // 1: z written with cp.async.bulk from the staging buffers
+    int tma_store;   // 1: z staged in shared memory and written with cp.async.bulk
+    int lockstep;    // 1: static unit assignment with a CTA barrier per round; 0: dynamic unit counter
+    int dbg_skip;    // tuning only (results invalid): bit0 skip logits, bit1 skip solver, bit2 skip cross pass
 };
 
 __host__ __device__ constexpr int round_up_c(int x, int a) { return (x + a - 1) / a * a; }
 
 // Shared-memory carve-up, identical on host (sizing) and device (pointers). Offsets in bytes.
 struct SmemLayout {
-    int off_bar, off_M, off_V, off_e, off_vals, off_out, total;
+    int off_bar, off_M, off_V, off_e, off_vals, off_ids, off_out, total;
+    int m_bytes, v_bytes;  // bytes of the M / V pair tables (padded to 16 for the bulk copy)
     int mstr, vstr;    // float2 strides of the M / V pair tables (odd: conflict-free LDS.64 across a half-warp)
-    int stage_floats;  // floats per e stage
-    int vals_floats;   // floats per value stage
-    int out_floats;    // floats per output staging buffer
+    int slot_floats;   // floats per e slot
+    int rows_pad;      // ids / values entries per tile
+    int out_floats;    // floats per warp staging buffer
     __host__ __device__ static int up(int x, int a) { return (x + a - 1) / a * a; }
     __host__ __device__ SmemLayout(int FP, int E_lanes, int E_stride, int ES, const FwdParams &P) {
         mstr = E_lanes | 1;
         vstr = FP | 1;
-        off_bar = 0;
-        off_M = 128;
-        off_V = up(off_M + P.R2 * mstr * 8, 16);
-        off_e = up(off_V + P.R2 * vstr * 8, 128);
-        stage_floats = P.TS * P.F * E_stride;
-        off_vals = up(off_e + P.n_stages * stage_floats * 4, 16);
-        vals_floats = up(P.TS * P.F, 4);
-        off_out = up(off_vals + P.n_stages * vals_floats * 4, 128);
-        out_floats = up((P.NT / ES) * kNR * P.E, 4);
-        total = off_out + (P.tma_store ? 2 * out_floats * 4 : 0);
+        off_bar = 0;                                   // 3 * kMaxSlots + 1 mbarriers, then the unit counter
+        off_M = up((3 * kMaxSlots + 1) * 8 + 16, 128);
+        m_bytes = up(P.R2 * mstr * 8, 16);
+        v_bytes = up(P.R2 * vstr * 8, 16);
+        off_V = off_M + m_bytes;
+        off_e = up(off_V + v_bytes, 128);
+        slot_floats = P.SPG * P.F * E_stride;
+        rows_pad = up(P.SPG * P.F, 4);
+        off_vals = up(off_e + P.n_slots * slot_floats * 4, 16);
+        off_ids = up(off_vals + P.TPE * rows_pad * 4, 16);
+        off_out = up(off_ids + P.TPE * rows_pad * 4, 128);
+        out_floats = up((32 / ES) * kNR * P.E, 4);
+        total = off_out + (P.tma_store ? P.NW * out_floats * 4 : 0);
     }
 };
 
@@ -133,6 +147,41 @@ __device__ __forceinline__ void cross_pass(const float (&X)[kNR][FP], const floa
     }
 }
 
+// Gather of one tile into its slot, by one whole warp; ids / clamped values come from the epoch's preloaded arrays.
+template <int E_STRIDE>
+__device__ __forceinline__ void issue_tile_gather(const FwdParams &P, const SmemLayout &L, int lane, long long tile,
+                                                  int slot, const int *i_ep, const float *v_ep, float *es,
+                                                  uint64_t *bar_raw, uint64_t *bar_full) {
+    const int F = P.F, E = P.E;
+    const long long b0 = tile * P.SPG;
+    const int ts = (int)min((long long)P.SPG, P.B - b0);
+    const int n = ts * F;
+    float *e_st = es + slot * L.slot_floats;
+    if (P.tma_gather) {
+        if (lane == 0) mbar_arrive_expect_tx(&bar_raw[slot], (uint32_t)(n * P.row_bytes));
+        __syncwarp();
+        for (int idx = lane; idx < n; idx += 32)
+            tma_load_bulk(e_st + idx * E_STRIDE, P.table + (long long)i_ep[idx] * P.ld, (uint32_t)P.row_bytes,
+                          &bar_raw[slot]);
+    } else {
+        for (int idx = lane; idx < n; idx += 32) {
+            const float v = v_ep[idx];
+            const float *src = P.table + (long long)i_ep[idx] * P.ld;
+            float *dst = e_st + idx * E_STRIDE;
+            if (((E | (int)P.ld) & 1) == 0 && (reinterpret_cast<uintptr_t>(P.table) & 7) == 0) {
+                for (int x = 0; x < E; x += 2) {
+                    const float2 t = __ldg(reinterpret_cast<const float2 *>(src + x));
+                    *reinterpret_cast<float2 *>(dst + x) = make_float2(__fmul_rn(t.x, v), __fmul_rn(t.y, v));
+                }
+            } else {
+                for (int x = 0; x < E; ++x) dst[x] = __fmul_rn(__ldg(src + x), v);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full[slot]);  // rows are already scaled: the tile is ready
+    }
+}
+
 template <int FP, bool EXACT, int EC, int ES>
 __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid_constant__ FwdParams P) {
     static_assert(EC % 2 == 0, "EC must be even (float2/float4 shared-memory reads)");
@@ -140,278 +189,327 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
     static_assert(ES == 1 || ES == 2 || ES == 4 || ES == 8, "ES must be a power of two <= 8");
     constexpr int E_LANES = EC * ES;
     constexpr int E_STRIDE = round_up_c(E_LANES, 4);
+    constexpr int PPW = 32 / ES;  // row pairs per warp-unit
     extern __shared__ __align__(128) unsigned char smem[];
     const SmemLayout L(FP, E_LANES, E_STRIDE, ES, P);
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + L.off_bar);
-    uint64_t *bar_empty = bar_full + kMaxStages;
-    uint64_t *bar_raw = bar_empty + kMaxStages;
+    uint64_t *bar_empty = bar_full + kMaxSlots;
+    uint64_t *bar_raw = bar_empty + kMaxSlots;
+    uint64_t *bar_par = bar_raw + kMaxSlots;
+    int *next_unit = reinterpret_cast<int *>(bar_par + 1);
     float2 *Ms2 = reinterpret_cast<float2 *>(smem + L.off_M);
     float2 *Vs2 = reinterpret_cast<float2 *>(smem + L.off_V);
     float *es = reinterpret_cast<float *>(smem + L.off_e);
     float *vals = reinterpret_cast<float *>(smem + L.off_vals);
+    int *idsm = reinterpret_cast<int *>(smem + L.off_ids);
     float *outs = reinterpret_cast<float *>(smem + L.off_out);
 
     const int tid = threadIdx.x;
-    const int NT = P.NT;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int NW = P.NW, NS = P.n_slots, UPG = P.UPG, LOOK = P.look;
     const int F = P.F, E = P.E, R = P.R, R2 = P.R2;
     const EntmaxParams ep = P.ep;
 
     if (tid == 0) {
-        for (int s = 0; s < kMaxStages; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_raw[s], 1);
-            mbar_init(&bar_empty[s], NT / 32);
+            mbar_init(&bar_empty[s], UPG);
         }
+        mbar_init(bar_par, 1);
         mbar_fence_init();
+        // the pre-contracted parameter tables arrive by TMA while the ids are being preloaded
+        mbar_arrive_expect_tx(bar_par, (uint32_t)(L.m_bytes + L.v_bytes));
+        tma_load_bulk(Ms2, P.Mg2, (uint32_t)L.m_bytes, bar_par);
+        tma_load_bulk(Vs2, P.Vg2, (uint32_t)L.v_bytes, bar_par);
     }
-    for (int i = tid; i < R2 * L.mstr; i += blockDim.x) Ms2[i] = P.Mg2[i];
-    for (int i = tid; i < R2 * L.vstr; i += blockDim.x) Vs2[i] = P.Vg2[i];
-    for (int i = tid; i < P.n_stages * L.stage_floats; i += blockDim.x) es[i] = 0.f;  // pad lanes stay zero for good
+    for (int i = tid; i < NS * L.slot_floats; i += blockDim.x) es[i] = 0.f;  // pad lanes stay zero for good
     fence_proxy_async_smem();
-    __syncthreads();
 
-    if (tid >= NT) {
-        // ===================================================== producer warp
-        const int lane = tid - NT;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
-            const int s = it % P.n_stages;
-            const uint32_t ph = (uint32_t)(it / P.n_stages) & 1u;
-            mbar_wait(&bar_empty[s], ph ^ 1u);
-            const long long b0 = (long long)tile * P.TS;
-            const int ts = (int)min((long long)P.TS, P.B - b0);
-            const int n = ts * F;
-            const long long base = b0 * F;
-            float *e_st = es + s * L.stage_floats;
-            float *v_st = vals + s * L.vals_floats;
-            if (P.tma_gather && lane == 0) mbar_arrive_expect_tx(&bar_raw[s], (uint32_t)(n * P.row_bytes));
-            __syncwarp();
-            for (int idx = lane; idx < n; idx += 32) {
-                long long id = P.ids_i32 ? (long long)reinterpret_cast<const int *>(P.ids)[base + idx]
-                                         : reinterpret_cast<const long long *>(P.ids)[base + idx];
-                float v = P.values[base + idx];
-                if (P.clamp) {  // armnet.py:82 -- in place on the caller's tensor
-                    const float vc = fminf(fmaxf(v, P.clamp_lo), P.clamp_hi);
-                    if (P.clamp_inplace && vc != v) P.values[base + idx] = vc;
-                    v = vc;
-                }
-                if ((unsigned long long)id >= (unsigned long long)P.V) {  // reference: IndexError (layers.py:20)
-                    if (P.err_flag) atomicOr(P.err_flag, 1);
-                    id = 0;
-                    v = 0.f;
-                }
-                const float *src = P.table + id * P.ld;
-                float *dst = e_st + idx * E_STRIDE;
-                if (P.tma_gather) {
-                    v_st[idx] = v;
-                    tma_load_bulk(dst, src, (uint32_t)P.row_bytes, &bar_raw[s]);
-                } else if (((E | (int)P.ld) & 1) == 0 && (reinterpret_cast<uintptr_t>(P.table) & 7) == 0) {
-                    for (int x = 0; x < E; x += 2) {
-                        const float2 t = __ldg(reinterpret_cast<const float2 *>(src + x));
-                        *reinterpret_cast<float2 *>(dst + x) = make_float2(__fmul_rn(t.x, v), __fmul_rn(t.y, v));
-                    }
-                } else {
-                    for (int x = 0; x < E; ++x) dst[x] = __fmul_rn(__ldg(src + x), v);
-                }
+    // tiles of this CTA: blockIdx.x + i * gridDim.x, i in [0, n_local)
+    const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int rows_per_tile = P.SPG * F;
+
+    const int c = lane % ES;   // which E-chunk of the pair this lane owns
+    const int pl = lane / ES;  // pair slot inside the unit
+    float *ost_base = outs + warp * L.out_floats;
+
+    for (int ep0 = 0; ep0 < n_local; ep0 += P.TPE) {
+    const int ep_tiles = min(P.TPE, n_local - ep0);
+    // ---- epoch start: every warp is done with the previous epoch; preload ids / clamped values of this one
+    __syncthreads();
+    for (int q = tid; q < ep_tiles * rows_per_tile; q += blockDim.x) {
+        const int tl = q / rows_per_tile, idx = q - tl * rows_per_tile;
+        const long long row = ((long long)blockIdx.x + (long long)(ep0 + tl) * gridDim.x) * rows_per_tile + idx;
+        long long id = 0;
+        float v = 0.f;
+        if (row < P.B * F) {
+            id = P.ids_i32 ? (long long)reinterpret_cast<const int *>(P.ids)[row]
+                           : reinterpret_cast<const long long *>(P.ids)[row];
+            v = P.values[row];
+            if (P.clamp) {  // armnet.py:82 -- in place on the caller's tensor
+                const float vc = fminf(fmaxf(v, P.clamp_lo), P.clamp_hi);
+                if (P.clamp_inplace && vc != v) P.values[row] = vc;
+                v = vc;
             }
+            if ((unsigned long long)id >= (unsigned long long)P.V) {  // reference: IndexError (layers.py:20)
+                if (P.err_flag) atomicOr(P.err_flag, 1);
+                id = 0;
+                v = 0.f;
+            }
+        }
+        idsm[tl * L.rows_pad + idx] = (int)id;
+        vals[tl * L.rows_pad + idx] = v;
+    }
+    if (tid == 0) *next_unit = ep0 * UPG;
+    __syncthreads();
+    if (ep0 == 0) mbar_wait(bar_par, 0);  // parameter tables have landed
+    // prologue of the epoch: its first LOOK tiles are fetched right away, one warp per tile
+    for (int t = warp; t < LOOK && t < ep_tiles; t += NW) {
+        const int j = ep0 + t;
+        const int sj = j % NS, use = j / NS;
+        if (use > 0) mbar_wait(&bar_empty[sj], (uint32_t)(use - 1) & 1u);
+        issue_tile_gather<E_STRIDE>(P, L, lane, (long long)blockIdx.x + (long long)j * gridDim.x, sj,
+                                    idsm + t * L.rows_pad, vals + t * L.rows_pad, es, bar_raw, bar_full);
+    }
+    const int u_end = (ep0 + ep_tiles) * UPG;
+
+    // Units are handed out in increasing order, either from a shared counter (a warp delayed by bookkeeping simply
+    // takes fewer units) or round-robin with a CTA barrier per round (lockstep).
+    const bool lockstep = P.lockstep != 0;
+    for (int round = 0;; ++round) {
+        int u;
+        if (lockstep) {
+            if (ep0 * UPG + round * NW >= u_end) break;
+            named_bar_sync(1, NW * 32);
+            u = ep0 * UPG + round * NW + warp;
+            if (u >= u_end) continue;
+        } else {
+            u = 0;
+            if (lane == 0) u = atomicAdd(next_unit, 1);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= u_end) break;
+        }
+        const int i = u / UPG;      // local tile index
+        const int k = u - i * UPG;  // unit inside the tile
+        const int slot = i % NS;
+        const uint32_t ph = (uint32_t)(i / NS) & 1u;
+        const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+        const long long b0 = tile * P.SPG;
+        const int ts = (int)min((long long)P.SPG, P.B - b0);
+
+        if (k == 0) {
+            // (a) own tile: rows landed -> e = row * v (layers.py:21) in place, then release it to every consumer
             if (P.tma_gather) {
-                mbar_wait(&bar_raw[s], ph);
-                __syncwarp();
-                // e = row * v (layers.py:21), in place, float4 chunks of the rows that just landed
+                mbar_wait(&bar_raw[slot], ph);
                 constexpr int C4 = E_STRIDE / 4;
-                float4 *e4 = reinterpret_cast<float4 *>(e_st);
-                for (int j = lane; j < n * C4; j += 32) {
-                    const float v = v_st[j / C4];
-                    float4 t = e4[j];
+                float4 *e4 = reinterpret_cast<float4 *>(es + slot * L.slot_floats);
+                const float *v_st = vals + (i - ep0) * L.rows_pad;
+                const int n = ts * F;
+                for (int q = lane; q < n * C4; q += 32) {
+                    const float v = v_st[q / C4];
+                    float4 t = e4[q];
                     t.x = __fmul_rn(t.x, v);
                     t.y = __fmul_rn(t.y, v);
                     t.z = __fmul_rn(t.z, v);
                     t.w = __fmul_rn(t.w, v);
-                    e4[j] = t;
+                    e4[q] = t;
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[slot]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_full[s]);
+            // (b) fetch the tile LOOK ahead into its slot, once that slot's previous tile is fully consumed
+            const int j = i + LOOK;
+            if (j < ep0 + ep_tiles) {
+                const int sj = j % NS;
+                const int use = j / NS;
+                if (use > 0) mbar_wait(&bar_empty[sj], (uint32_t)(use - 1) & 1u);
+                issue_tile_gather<E_STRIDE>(P, L, lane, (long long)blockIdx.x + (long long)j * gridDim.x, sj,
+                                            idsm + (j - ep0) * L.rows_pad, vals + (j - ep0) * L.rows_pad, es, bar_raw,
+                                            bar_full);
+            }
         }
-        return;
-    }
+        mbar_wait(&bar_full[slot], ph);
 
-    // ========================================================= consumer threads
-    const int ppp = NT / ES;  // row pairs per pass
-    const int c = tid % ES;   // which E-chunk of the pair this lane owns
-    const int rl = tid / ES;  // pair slot inside the pass
-    int it = 0;
-    int ob = 0;
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
-        const int s = it % P.n_stages;
-        const uint32_t ph = (uint32_t)(it / P.n_stages) & 1u;
-        const long long b0 = (long long)tile * P.TS;
-        const int ts = (int)min((long long)P.TS, P.B - b0);
-        const int n_pairs = ts * R2;
-        const float *e_st = es + s * L.stage_floats;
-        mbar_wait(&bar_full[s], ph);
+        const int n_pairs = ts * R2;    // row pairs in this tile
+        const int p_first = k * PPW;    // first pair of this unit
+        const int pi = p_first + pl;
+        const bool valid = pi < n_pairs;
+        const int pic = valid ? pi : n_pairs - 1;  // idle lanes redo the last pair (votes/shuffles stay full-warp)
+        const int bl = pic / R2;
+        const int j2 = pic - bl * R2;
+        const int r0 = 2 * j2;
+        const bool has1 = (r0 + 1 < R);             // odd R: the last pair's second row is a dummy
+        const long long grow = (b0 + bl) * R + r0;  // global index of the pair's first row
+        const float *eb = es + slot * L.slot_floats + bl * F * E_STRIDE + c * EC;
 
-        for (int pb = 0; pb < n_pairs; pb += ppp) {
-            const int pi = pb + rl;
-            const bool valid = pi < n_pairs;
-            const int pic = valid ? pi : n_pairs - 1;  // idle lanes redo the last pair (votes/shuffles stay full-warp)
-            const int bl = pic / R2;
-            const int j = pic - bl * R2;
-            const int r0 = 2 * j;
-            const bool has1 = (r0 + 1 < R);             // odd R: the last pair's second row is a dummy
-            const long long grow = (b0 + bl) * R + r0;  // global index of the pair's first row
-            const float *eb = e_st + bl * F * E_STRIDE + c * EC;
-
-            // ---- X = (alpha-1) * g = e . M' (armnet.py:33-34 and entmax.py:42; both scalings are folded into M')
-            float X[kNR][FP];
-            {
-                float2 Mr[EC];
-                const float2 *mrow = Ms2 + j * L.mstr + c * EC;
+        // ---- X = (alpha-1) * g = e . M' (armnet.py:33-34 and entmax.py:42; both scalings are folded into M')
+        float X[kNR][FP];
+        if (P.dbg_skip & 1) {
 #pragma unroll
-                for (int x = 0; x < EC; ++x) Mr[x] = mrow[x];
+            for (int f = 0; f < FP; ++f) X[0][f] = X[1][f] = (float)(f + lane) * 1e-3f;
+        } else {
+            float2 Mr[EC];
+            const float2 *mrow = Ms2 + j2 * L.mstr + c * EC;
 #pragma unroll
-                for (int f = 0; f < FP; ++f) {
-                    if (EXACT || f < F) {
-                        float e[EC];
-                        load_e_chunk<EC>(eb + f * E_STRIDE, e);
-                        float a0 = 0.f, a1 = 0.f;
+            for (int x = 0; x < EC; ++x) Mr[x] = mrow[x];
 #pragma unroll
-                        for (int x = 0; x < EC; ++x) {
-                            a0 = fmaf(e[x], Mr[x].x, a0);
-                            a1 = fmaf(e[x], Mr[x].y, a1);
-                        }
-#pragma unroll
-                        for (int m = 1; m < ES; m <<= 1) {
-                            a0 += __shfl_xor_sync(0xffffffffu, a0, m);
-                            a1 += __shfl_xor_sync(0xffffffffu, a1, m);
-                        }
-                        X[0][f] = a0;
-                        X[1][f] = a1;
-                    } else {
-                        X[0][f] = neg_inf();
-                        X[1][f] = neg_inf();
-                    }
-                }
-            }
-            if (P.out_g != nullptr && valid && c == 0) {  // validation output: g = X / (alpha-1)
-#pragma unroll
-                for (int f = 0; f < FP; ++f) {
-                    if (EXACT || f < F) {
-                        P.out_g[grow * F + f] = X[0][f] * P.g_unscale;
-                        if (has1) P.out_g[(grow + 1) * F + f] = X[1][f] * P.g_unscale;
-                    }
-                }
-            }
-            // The cross pass re-reads e from shared memory; without this compiler barrier nvcc keeps all loaded e
-            // values alive across the solver (and spills them) instead of re-issuing 29-cycle LDS.
-            asm volatile("" ::: "memory");
-
-            // ---- thresholds (entmax.py:44-61), both rows of the pair together
-            float tau[kNR];
-            entmax_solve_tau<kNR, FP, EXACT>(X, F, ep, tau);
-            asm volatile("" ::: "memory");
-
-            // ---- gates, gates*values and the log-space product s = sum_f w_f e_f (armnet.py:36,87)
-            float acc[kNR][EC];
-#pragma unroll
-            for (int x = 0; x < EC; ++x) acc[0][x] = acc[1][x] = 0.f;
-            float S[kNR] = {0.f, 0.f};
-            const float2 *vrow = Vs2 + j * L.vstr;
-            switch (ep.mode) {
-                case POW_SOFTMAX: cross_pass<POW_SOFTMAX, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
-                case POW_LINEAR: cross_pass<POW_LINEAR, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
-                case POW_SQUARE: cross_pass<POW_SQUARE, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
-                default: cross_pass<POW_GENERAL, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
-            }
-            const float inv0 = __frcp_rn(S[0]);  // entmax.py:63-64 renormalisation
-            const float inv1 = __frcp_rn(S[1]);
-
-            if (valid && c == 0 && (P.out_tau != nullptr || P.out_p != nullptr)) {
-                if (P.out_tau != nullptr) {
-                    P.out_tau[2 * grow + 0] = tau[0];
-                    P.out_tau[2 * grow + 1] = S[0];
-                    if (has1) {
-                        P.out_tau[2 * grow + 2] = tau[1];
-                        P.out_tau[2 * grow + 3] = S[1];
-                    }
-                }
-                if (P.out_p != nullptr) {
-#pragma unroll
-                    for (int f = 0; f < FP; ++f) {  // static indices only: X must stay in registers
-                        if (EXACT || f < F) {
-                            P.out_p[grow * F + f] = __fdiv_rn(gate_unnorm_rt(X[0][f], tau[0], ep), S[0]);
-                            if (has1) P.out_p[(grow + 1) * F + f] = __fdiv_rn(gate_unnorm_rt(X[1][f], tau[1], ep), S[1]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int x = 0; x < EC; ++x) {
-                acc[0][x] *= inv0;
-                acc[1][x] *= inv1;
-            }
-            if (P.out_s != nullptr && valid) {
-#pragma unroll
-                for (int x = 0; x < EC; ++x) {
-                    if (c * EC + x < E) {
-                        P.out_s[grow * E + c * EC + x] = acc[0][x];
-                        if (has1) P.out_s[(grow + 1) * E + c * EC + x] = acc[1][x];
-                    }
-                }
-            }
-
-            // ---- z = exp(s) (armnet.py:86) [then eval-mode arm_bn, armnet.py:89], written as [b][r][0:E]
-#pragma unroll
-            for (int x = 0; x < EC; ++x) {
-                acc[0][x] = expf(acc[0][x]);
-                acc[1][x] = expf(acc[1][x]);
-            }
-            if (P.post_scale != nullptr) {
-                const int r1 = has1 ? r0 + 1 : r0;
-                const float m0 = __ldg(P.post_mean + r0), a0 = __ldg(P.post_scale + r0), h0 = __ldg(P.post_shift + r0);
-                const float m1 = __ldg(P.post_mean + r1), a1 = __ldg(P.post_scale + r1), h1 = __ldg(P.post_shift + r1);
-#pragma unroll
-                for (int x = 0; x < EC; ++x) {
-                    acc[0][x] = fmaf(acc[0][x] - m0, a0, h0);
-                    acc[1][x] = fmaf(acc[1][x] - m1, a1, h1);
-                }
-            }
-            if (P.tma_store) {  // R is even here: the pair's 2E outputs are contiguous
-                float *ost = outs + ob * L.out_floats + rl * (kNR * E) + c * EC;
-                if (valid) {
+            for (int f = 0; f < FP; ++f) {
+                if (EXACT || f < F) {
+                    float e[EC];
+                    load_e_chunk<EC>(eb + f * E_STRIDE, e);
+                    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
                     for (int x = 0; x < EC; ++x) {
-                        if (c * EC + x < E) {
-                            ost[x] = acc[0][x];
-                            ost[E + x] = acc[1][x];
-                        }
+                        a0 = fmaf(e[x], Mr[x].x, a0);
+                        a1 = fmaf(e[x], Mr[x].y, a1);
                     }
-                }
-                if (tid == 0) tma_store_wait_read<0>();  // the buffer the NEXT pass writes is free again
-                fence_proxy_async_smem();
-                named_bar_sync(1, NT);
-                if (tid == 0) {
-                    const int pairs_here = min(ppp, n_pairs - pb);
-                    tma_store_bulk(P.out_z + ((b0 * R + 2LL * pb) * (long long)E), outs + ob * L.out_floats,
-                                   (uint32_t)(pairs_here * kNR * E * 4));
-                    tma_store_commit();
-                }
-                ob ^= 1;
-            } else if (valid) {
-                float *dst = P.out_z + grow * E + c * EC;
 #pragma unroll
-                for (int x = 0; x < EC; ++x) {
-                    if (c * EC + x < E) {
-                        dst[x] = acc[0][x];
-                        if (has1) dst[E + x] = acc[1][x];
+                    for (int m = 1; m < ES; m <<= 1) {
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, m);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, m);
+                    }
+                    X[0][f] = a0;
+                    X[1][f] = a1;
+                } else {
+                    X[0][f] = neg_inf();
+                    X[1][f] = neg_inf();
+                }
+            }
+        }
+        if (P.out_g != nullptr && valid && c == 0) {  // validation output: g = X / (alpha-1)
+#pragma unroll
+            for (int f = 0; f < FP; ++f) {
+                if (EXACT || f < F) {
+                    P.out_g[grow * F + f] = X[0][f] * P.g_unscale;
+                    if (has1) P.out_g[(grow + 1) * F + f] = X[1][f] * P.g_unscale;
+                }
+            }
+        }
+        // The cross pass re-reads e from shared memory; without this compiler barrier nvcc keeps all loaded e values
+        // alive across the solver (and spills them) instead of re-issuing 29-cycle LDS.
+        asm volatile("" ::: "memory");
+
+        // ---- thresholds (entmax.py:44-61), both rows of the pair together
+        float tau[kNR];
+        if (P.dbg_skip & 2) {
+            tau[0] = X[0][0] - 0.05f;
+            tau[1] = X[1][0] - 0.05f;
+        } else {
+            entmax_solve_tau<kNR, FP, EXACT>(X, F, ep, tau);
+        }
+        asm volatile("" ::: "memory");
+
+        // ---- gates, gates*values and the log-space product s = sum_f w_f e_f (armnet.py:36,87)
+        float acc[kNR][EC];
+#pragma unroll
+        for (int x = 0; x < EC; ++x) acc[0][x] = acc[1][x] = 0.f;
+        float S[kNR] = {0.f, 0.f};
+        const float2 *vrow = Vs2 + j2 * L.vstr;
+        if (P.dbg_skip & 4) {
+            S[0] = S[1] = 1.f + tau[0];
+            acc[0][0] = X[0][1] + X[0][FP - 1];
+            acc[1][0] = X[1][1] + X[1][FP - 1];
+        } else switch (ep.mode) {
+            case POW_SOFTMAX: cross_pass<POW_SOFTMAX, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
+            case POW_LINEAR: cross_pass<POW_LINEAR, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
+            case POW_SQUARE: cross_pass<POW_SQUARE, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
+            default: cross_pass<POW_GENERAL, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
+        }
+        // every lane is done reading the tile: hand the slot back (one arrival per unit)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[slot]);
+
+        const float inv0 = __frcp_rn(S[0]);  // entmax.py:63-64 renormalisation
+        const float inv1 = __frcp_rn(S[1]);
+
+        if (valid && c == 0 && (P.out_tau != nullptr || P.out_p != nullptr)) {
+            if (P.out_tau != nullptr) {
+                P.out_tau[2 * grow + 0] = tau[0];
+                P.out_tau[2 * grow + 1] = S[0];
+                if (has1) {
+                    P.out_tau[2 * grow + 2] = tau[1];
+                    P.out_tau[2 * grow + 3] = S[1];
+                }
+            }
+            if (P.out_p != nullptr) {
+#pragma unroll
+                for (int f = 0; f < FP; ++f) {  // static indices only: X must stay in registers
+                    if (EXACT || f < F) {
+                        P.out_p[grow * F + f] = __fdiv_rn(gate_unnorm_rt(X[0][f], tau[0], ep), S[0]);
+                        if (has1) P.out_p[(grow + 1) * F + f] = __fdiv_rn(gate_unnorm_rt(X[1][f], tau[1], ep), S[1]);
                     }
                 }
             }
         }
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&bar_empty[s]);
-    }
-    if (P.tma_store && tid == 0) tma_store_wait_all<0>();
+#pragma unroll
+        for (int x = 0; x < EC; ++x) {
+            acc[0][x] *= inv0;
+            acc[1][x] *= inv1;
+        }
+        if (P.out_s != nullptr && valid) {
+#pragma unroll
+            for (int x = 0; x < EC; ++x) {
+                if (c * EC + x < E) {
+                    P.out_s[grow * E + c * EC + x] = acc[0][x];
+                    if (has1) P.out_s[(grow + 1) * E + c * EC + x] = acc[1][x];
+                }
+            }
+        }
+
+        // ---- z = exp(s) (armnet.py:86) [then eval-mode arm_bn, armnet.py:89], written as [b][r][0:E]
+#pragma unroll
+        for (int x = 0; x < EC; ++x) {
+            acc[0][x] = expf(acc[0][x]);
+            acc[1][x] = expf(acc[1][x]);
+        }
+        if (P.post_scale != nullptr) {
+            const int r1 = has1 ? r0 + 1 : r0;
+            const float m0 = __ldg(P.post_mean + r0), a0 = __ldg(P.post_scale + r0), h0 = __ldg(P.post_shift + r0);
+            const float m1 = __ldg(P.post_mean + r1), a1 = __ldg(P.post_scale + r1), h1 = __ldg(P.post_shift + r1);
+#pragma unroll
+            for (int x = 0; x < EC; ++x) {
+                acc[0][x] = fmaf(acc[0][x] - m0, a0, h0);
+                acc[1][x] = fmaf(acc[1][x] - m1, a1, h1);
+            }
+        }
+        // the unit's rows [2*p_first, 2*min(p_first+PPW, n_pairs)) of the tile are contiguous in out_z when R is even
+        const int pairs_here = min(PPW, n_pairs - p_first);
+        float *gdst = P.out_z + (b0 * R + 2LL * p_first) * (long long)E;
+        const uint32_t bytes = (uint32_t)(pairs_here * kNR * E * 4);
+        if (P.tma_store && ((bytes | (uint32_t)reinterpret_cast<uintptr_t>(gdst)) & 15u) == 0) {
+            if (lane == 0) tma_store_wait_read<0>();  // this warp's previous bulk store has drained the buffer
+            __syncwarp();
+            float *ost = ost_base + pl * (kNR * E) + c * EC;
+            if (valid) {
+#pragma unroll
+                for (int x = 0; x < EC; ++x) {
+                    if (c * EC + x < E) {
+                        ost[x] = acc[0][x];
+                        ost[E + x] = acc[1][x];
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_bulk(gdst, ost_base, bytes);
+                tma_store_commit();
+            }
+        } else if (valid) {
+            float *dst = P.out_z + grow * E + c * EC;
+#pragma unroll
+            for (int x = 0; x < EC; ++x) {
+                if (c * EC + x < E) {
+                    dst[x] = acc[0][x];
+                    if (has1) dst[E + x] = acc[1][x];
+                }
+            }
+        }
+    }  // units of the epoch
+    }  // epochs
+    if (P.tma_store && lane == 0) tma_store_wait_all<0>();
 }
 
 // One compiled shape of the kernel.

@@ -38,6 +38,11 @@ WORKLOADS = {
                mlp_nlayer=3, mlp_nhid=200),
     'c4': dict(model='armnet', nfield=39, nfeat=1000000, nemb=16, nhead=4, nhid=128, alpha=1.7, bsz=4096,
                mlp_nlayer=2, mlp_nhid=256),
+    # tuning probes (not BASELINE configs): C2a with fewer fields -> smaller unrolled kernel body
+    'f20': dict(model='armnet', nfield=20, nfeat=1000000, nemb=10, nhead=4, nhid=128, alpha=1.7, bsz=4096,
+                mlp_nlayer=2, mlp_nhid=256),
+    'f10': dict(model='armnet', nfield=10, nfeat=1000000, nemb=10, nhead=4, nhid=128, alpha=1.7, bsz=4096,
+                mlp_nlayer=2, mlp_nhid=256),
     'c1': dict(model='armnet_1h', nfield=10, nfeat=5382, nemb=10, nhead=1, nhid=10, alpha=1.7, bsz=4096,
                mlp_nlayer=2, mlp_nhid=256),
 }
