@@ -1,0 +1,84 @@
+"""Data-parallel plumbing for the hot path: one process per GPU, batch-sharded, parameters replicated.
+
+The forward path needs NO collective (every sample depends only on its own ids/values and on replicated parameters,
+armnet.py:82-87).  Training adds exactly one all-reduce per step over a single flat fp32 gradient bucket, after which
+the gradient is averaged and clamped to [-1, 1] -- the reference clamps every parameter gradient with a hook
+(train.py:64-65); clamping AFTER the all-reduce keeps N ranks x (B/N) samples equivalent to the reference's single
+process on the concatenated batch.  Works with any torch.distributed backend (NCCL on the B200 box, gloo in CPU tests).
+"""
+from typing import Dict, Iterable, List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rows [lo, hi) of a global batch owned by `rank`: contiguous, sizes differ by at most one, empty allowed."""
+    base, rem = divmod(n_rows, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[str, torch.Tensor]:
+    """Slice every [B, ...] tensor of a {'id','value','y'} batch (data_loader.py:52-55) to this rank's rows."""
+    n = next(iter(batch.values())).shape[0]
+    lo, hi = shard_bounds(n, rank, world)
+    return {k: v[lo:hi] for k, v in batch.items()}
+
+
+class GradAllReducer:
+    """One flat fp32 bucket for all parameter gradients; step(): all-reduce(sum) -> /world -> clamp -> scatter back."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], clamp: float = 1.0, group=None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.clamp = clamp
+        self.group = group
+        n = sum(p.numel() for p in self.params)
+        p0 = self.params[0]
+        self.bucket = torch.zeros(n, dtype=torch.float32, device=p0.device)
+        self.views = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.bucket[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def numel(self) -> int:
+        return self.bucket.numel()
+
+    @torch.no_grad()
+    def step(self, weight: float = 1.0) -> None:
+        """`weight` = this rank's share of the global batch times world size (1.0 for equal shards), so the result
+        is the gradient of the mean loss over the concatenated batch."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            else:
+                v.copy_(p.grad)
+        if weight != 1.0:
+            self.bucket.mul_(weight)
+        if world > 1:
+            dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, group=self.group)
+            self.bucket.div_(world)
+        if self.clamp is not None:
+            self.bucket.clamp_(-self.clamp, self.clamp)      # train.py:65 semantics at global-batch level
+        for p, v in zip(self.params, self.views):
+            p.grad = v                                        # optimizer reads straight from the bucket
+
+
+@torch.no_grad()
+def broadcast_buffers(model: torch.nn.Module, src: int = 0, group=None) -> None:
+    """BatchNorm running statistics are per-replica in DP (the reference has no SyncBN); make them rank `src`'s
+    before evaluation / checkpointing."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for b in model.buffers():
+        dist.broadcast(b, src=src, group=group)
+
+
+def max_over_ranks(value: float, device, group=None) -> float:
+    """Timing rule of bench.py: a multi-GPU number is the MAX over ranks."""
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

@@ -97,3 +97,26 @@ def test_create_model_surface():
     args.model = 'nope'
     with pytest.raises(ValueError, match='unknown model'):
         ab.create_model(args, logging.getLogger('t'))
+
+
+def test_train_cli_surface_and_helpers(tmp_path):
+    """train.py keeps the reference's flags/defaults (train.py:15-50) and accepts run.sh's stale aliases."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('armnet_train_cli', os.path.join(ROOT, 'train.py'))
+    t = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(t)          # guarded by __main__: importing must not parse argv or load data
+    a = t.get_args([])
+    assert (a.model, a.nfeat, a.nfield, a.nemb, a.h, a.nattn_head, a.alpha) == ('armnet', 5500, 10, 10, 128, 4, 1.7)
+    assert (a.mlp_nlayer, a.mlp_nhid, a.batch_size, a.lr, a.seed, a.patience) == (2, 256, 4096, 0.003, 2025, 1)
+    b = t.get_args(['--nlayer', '3', '--mlp_hid', '200', '--dnn_hid', '200', '--model', 'armnet_1h'])
+    assert (b.mlp_nlayer, b.mlp_nhid, b.dnn_nhid) == (3, 200, 200)
+    # libsvm parsing incl. a malformed line (skipped like data_loader.py:37-44)
+    f = tmp_path / 'x.libsvm'
+    f.write_text('1 3:1 7:0.5\n0 2:1 9:1\nbroken line\n1 4:x 5:1\n')
+    ids, vals, y = t.load_libsvm(str(f), 2)
+    assert ids.tolist() == [[3, 7], [2, 9]] and vals[0, 1].item() == 0.5 and y.tolist() == [1.0, 0.0]
+    # AUC rank statistic
+    logits = torch.tensor([0.1, 0.4, 0.35, 0.8])
+    target = torch.tensor([0., 0., 1., 1.])
+    assert abs(t.auc_on_device(logits, target) - 0.75) < 1e-12
+    assert t.auc_on_device(logits, torch.ones(4)) == 0.0

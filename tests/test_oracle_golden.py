@@ -53,3 +53,22 @@ def test_reference_init_state_shapes():
     st1 = oracle.reference_init_state('armnet_1h', 10, 5382, 10, 1, 10)
     out = oracle.forward(st1, 1.7, torch.randint(0, 5382, (4, 10)), torch.ones(4, 10))
     assert out['z'].shape == (4, 10, 10)
+
+
+def test_c_oracle_matches_reference(golden):
+    """The plain-C restatement (oracle/armnet_oracle.c) against the reference fixtures: gather bit-exact,
+    gates within 2e-6, logits / sums / output within 1e-6 norm-relative (libm vs ATen pow/exp: <= 2 ulp)."""
+    import numpy as np
+    from conftest import norm_rel
+    from oracle import c_oracle
+    vals = golden.values.clone().numpy()
+    st = {k: v.numpy() for k, v in golden.state.items()}
+    out = c_oracle.hot_path(st, float(golden.cfg['alpha']), golden.ids.numpy(), vals)
+    B = golden.ids.shape[0]
+    assert np.array_equal(vals, golden.out['values_after'].numpy())
+    assert np.array_equal(out['e'], golden.out['e'].numpy())
+    ref = {k: golden.out[k].reshape(B, -1, golden.out[k].shape[-1]) for k in ('g', 'p', 's', 'z')}
+    assert norm_rel(out['g'], ref['g']) <= 1e-6
+    assert np.abs(out['p'] - ref['p'].numpy()).max() <= 2e-6
+    assert norm_rel(out['s'], ref['s']) <= 2e-6
+    assert norm_rel(out['z'], ref['z']) <= 1e-6
