@@ -201,7 +201,6 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
         if (nw >= 1 && nw <= kMaxWarps) P.NW = nw;
     }
     P.lockstep = getenv("ARMNET_DYNAMIC") ? 0 : 1;
-    P.dbg_skip = getenv("ARMNET_DEBUG_SKIP") ? atoi(getenv("ARMNET_DEBUG_SKIP")) : 0;
 
     // ---- TMA eligibility
     P.row_bytes = round_up(E * 4, 16);

@@ -71,7 +71,6 @@ struct FwdParams {
     int row_bytes;
     int tma_store;   // 1: z staged in shared memory and written with cp.async.bulk
     int lockstep;    // 1: static unit assignment with a CTA barrier per round; 0: dynamic unit counter
-    int dbg_skip;    // tuning only (results invalid): bit0 skip logits, bit1 skip solver, bit2 skip cross pass
 };
 
 __host__ __device__ constexpr int round_up_c(int x, int a) { return (x + a - 1) / a * a; }
@@ -346,10 +345,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
 
         // ---- X = (alpha-1) * g = e . M' (armnet.py:33-34 and entmax.py:42; both scalings are folded into M')
         float X[kNR][FP];
-        if (P.dbg_skip & 1) {
-#pragma unroll
-            for (int f = 0; f < FP; ++f) X[0][f] = X[1][f] = (float)(f + lane) * 1e-3f;
-        } else {
+        {
             float2 Mr[EC];
             const float2 *mrow = Ms2 + j2 * L.mstr + c * EC;
 #pragma unroll
@@ -393,12 +389,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
 
         // ---- thresholds (entmax.py:44-61), both rows of the pair together
         float tau[kNR];
-        if (P.dbg_skip & 2) {
-            tau[0] = X[0][0] - 0.05f;
-            tau[1] = X[1][0] - 0.05f;
-        } else {
-            entmax_solve_tau<kNR, FP, EXACT>(X, F, ep, tau);
-        }
+        entmax_solve_tau<kNR, FP, EXACT>(X, F, ep, tau);
         asm volatile("" ::: "memory");
 
         // ---- gates, gates*values and the log-space product s = sum_f w_f e_f (armnet.py:36,87)
@@ -407,11 +398,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
         for (int x = 0; x < EC; ++x) acc[0][x] = acc[1][x] = 0.f;
         float S[kNR] = {0.f, 0.f};
         const float2 *vrow = Vs2 + j2 * L.vstr;
-        if (P.dbg_skip & 4) {
-            S[0] = S[1] = 1.f + tau[0];
-            acc[0][0] = X[0][1] + X[0][FP - 1];
-            acc[1][0] = X[1][1] + X[1][FP - 1];
-        } else switch (ep.mode) {
+        switch (ep.mode) {
             case POW_SOFTMAX: cross_pass<POW_SOFTMAX, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
             case POW_LINEAR: cross_pass<POW_LINEAR, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
             case POW_SQUARE: cross_pass<POW_SQUARE, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;

@@ -46,6 +46,10 @@ WORKLOADS = {
     'c1': dict(model='armnet_1h', nfield=10, nfeat=5382, nemb=10, nhead=1, nhid=10, alpha=1.7, bsz=4096,
                mlp_nlayer=2, mlp_nhid=256),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of armnet_fwd_kernel from the committed `ncu --set full`
+# capture (profiles/r1_v3_fwd_summary.md): 21.9 MB read + 25.4 MB written. Below the algorithmic 92.2 MB because part
+# of the 84 MB output is still dirty in the 126 MB L2 when the kernel ends; no re-reads.
+NCU_TRAFFIC_BYTES = {'c2a': 47289344}
 METRIC = 'CTR samples/sec (bsz=4096, Criteo-shape) at 1/2/4/8 B200; HBM GB/s vs roofline'
 
 
@@ -292,7 +296,8 @@ def main():
         'config': dict(cfg, l2='flushed between timed steps (256 MiB memset outside the events)'
                        if flush is not None else 'not flushed'),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': abytes,
+                     'traffic': NCU_TRAFFIC_BYTES.get(args.workload), 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': abytes,
                      'kernel': 'armnet_fwd_kernel (+ attn_prepare_kernel, ~1% of the step)',
                      'note': 'path is FP32-issue/MUFU bound (entmax), not HBM bound; see DESIGN.md'},
         'e2e': {'value': w['bsz'] * args.steps * n / e2e_s, 'unit': 'samples/s',
