@@ -72,6 +72,8 @@ int make_entmax_params(float alpha, int F, int solver, int n_iter, EntmaxParams 
     ep->qm1 = q - 1.f;
     // entmax.py:18,47: (1/d) ** (alpha-1) with the scalar base cast to fp32.
     ep->cF = (float)pow((double)(float)(1.0 / (double)F), (double)am1);
+    ep->uni_k = ep->qm1 * 0.5f / ep->cF;
+    ep->uni_var = 0.04f * ep->cF * ep->cF / (float)F;
     if (solver == ARMNET_SOLVER_BISECT || q < 1.f) {
         ep->mode = POW_BISECT;  // alpha > 2: f is not convex, keep the reference's bracketing search
     } else if (q == 1.f) {

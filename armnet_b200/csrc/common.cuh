@@ -43,6 +43,8 @@ struct EntmaxParams {
     float qm1;       // q - 1
     float cF;        // F^-(alpha-1) = (1/d)^(alpha-1), the offset of tau_hi (entmax.py:47)
     float inv_F;     // 1 / F
+    float uni_k;     // (q-1) / (2 cF): second-order term of the near-uniform closed-form start
+    float uni_var;   // largest variance of X for which that start is tried: (0.2 cF)^2 / F
 };
 
 // Fills *ep for (alpha, F, solver). Returns ARMNET_OK or ARMNET_ERR_SHAPE.

@@ -29,8 +29,9 @@ __global__ void __launch_bounds__(kRowsPerCta) entmax_fwd_kernel(const float *__
         float X[1][FP];
 #pragma unroll
         for (int f = 0; f < FP; ++f) X[0][f] = (f < F) ? mine[f] * ep.am1 : neg_inf();  // entmax.py:42
-        float tau[1];
-        entmax_solve_tau<1, FP, false>(X, F, ep, tau);
+        float tau[1], mx[1], mean[1];
+        row_max_mean<FP, false>(X[0], F, ep, mx[0], mean[0]);
+        entmax_solve_tau<1, FP, false>(X, F, ep, mx, mean, tau);
         float s = 0.f;
 #pragma unroll
         for (int f = 0; f < FP; ++f) {

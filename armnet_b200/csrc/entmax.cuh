@@ -47,20 +47,33 @@ __device__ __forceinline__ float gate_unnorm_rt(float x, float tau, const Entmax
     }
 }
 
+// Row maximum and mean over the real fields (padded entries are -inf and excluded from the mean).
+template <int FP, bool EXACT>
+__device__ __forceinline__ void row_max_mean(const float (&X)[FP], int F, const EntmaxParams &ep, float &mx,
+                                             float &mean) {
+    mx = X[0];
+#pragma unroll
+    for (int f = 1; f < FP; ++f) mx = fmaxf(mx, X[f]);
+    float sum = 0.f;
+#pragma unroll
+    for (int f = 0; f < FP; ++f)
+        if (EXACT || f < F) sum += X[f];
+    mean = sum * ep.inv_F;
+}
+
 // X[n][f] = (alpha-1) * g[f] of row n for f < F (g itself for softmax), -inf for padded f >= F.
 // NR rows are solved together in one loop (their element-wise work interleaves: twice the ILP per thread); a row that
 // has converged keeps taking Newton steps until every row of every lane has, which only tightens it.
 // All 32 lanes of the warp must call this together (warp-uniform exit votes).
+// mx / mean: from row_max_mean.  `warm` (POW_GENERAL only): tau[] already holds a Newton iterate (from the fused
+// first pass of the caller); the bound-based start is skipped.
 template <int NR, int FP, bool EXACT>
 __device__ __forceinline__ void entmax_solve_tau(const float (&X)[NR][FP], int F, const EntmaxParams &ep,
-                                                 float (&tau)[NR]) {
-    float mx[NR];
+                                                 const float (&mx)[NR], const float (&mean)[NR], float (&tau)[NR],
+                                                 bool warm = false) {
+    if (!warm) {
 #pragma unroll
-    for (int n = 0; n < NR; ++n) {
-        mx[n] = X[n][0];
-#pragma unroll
-        for (int f = 1; f < FP; ++f) mx[n] = fmaxf(mx[n], X[n][f]);
-        tau[n] = mx[n];
+        for (int n = 0; n < NR; ++n) tau[n] = mx[n];
     }
     if (ep.mode == POW_SOFTMAX) return;
 
@@ -102,13 +115,9 @@ __device__ __forceinline__ void entmax_solve_tau(const float (&X)[NR][FP], int F
 
     // Lower bounds on the root: the max element alone gives tau >= max - 1; Jensen on the convex u^q
     // (q >= 1) gives tau >= mean - F^-(1/q) = mean - F^-(alpha-1).
+    if (!warm) {
 #pragma unroll
-    for (int n = 0; n < NR; ++n) {
-        float sum = 0.f;
-#pragma unroll
-        for (int f = 0; f < FP; ++f)
-            if (EXACT || f < F) sum += X[n][f];
-        tau[n] = fmaxf(mx[n] - 1.f, sum * ep.inv_F - ep.cF);
+        for (int n = 0; n < NR; ++n) tau[n] = fmaxf(mx[n] - 1.f, mean[n] - ep.cF);
     }
 
     constexpr int kMaxIt = 12;
@@ -188,6 +197,27 @@ __device__ __forceinline__ void entmax_solve_tau(const float (&X)[NR][FP], int F
             if (__all_sync(0xffffffffu, done)) break;
         }
     }
+}
+
+
+// Near-uniform rows (X_f = m + eps_f with |eps| << c = F^-(alpha-1)): expanding sum (c' + eps_f)^q = 1 to second order
+// gives tau = m - c + (q-1) var(eps) / (2c) + O(eps^3 / c^2).  Returns that start and whether every |eps_f| <= 0.2 c
+// (checked through F*var >= max eps^2).  The caller verifies the start with a Newton residual before trusting it.
+template <int FP, bool EXACT>
+__device__ __forceinline__ bool entmax_uniform_start(const float (&X)[FP], int F, const EntmaxParams &ep, float mx,
+                                                     float mean, float &tau0) {
+    float sd2 = 0.f;  // second moment of d_f = X_f - max (small numbers: no cancellation at large |X|)
+#pragma unroll
+    for (int f = 0; f < FP; ++f) {
+        if (EXACT || f < F) {
+            const float d = X[f] - mx;
+            sd2 = fmaf(d, d, sd2);
+        }
+    }
+    const float md = mean - mx;
+    const float var = fmaxf(fmaf(-md, md, sd2 * ep.inv_F), 0.f);
+    tau0 = mean - ep.cF + ep.uni_k * var;
+    return var <= ep.uni_var;
 }
 
 }  // namespace armnet

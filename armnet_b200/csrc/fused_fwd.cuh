@@ -103,6 +103,14 @@ struct SmemLayout {
     }
 };
 
+// Returns p unchanged but opaque to the optimiser. Each phase (logits / fused first pass / cross pass) re-reads the
+// e tile from shared memory through its own opaque pointer; otherwise nvcc value-numbers the loads across phases,
+// keeps F*E values alive through the solver and spills them to local memory.
+__device__ __forceinline__ const float *opaque_ptr(const float *p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
+
 // EC consecutive floats of one e row, as float4s plus a float2 tail (EC even).
 template <int EC>
 __device__ __forceinline__ void load_e_chunk(const float *src, float (&e)[EC]) {
@@ -136,6 +144,39 @@ __device__ __forceinline__ void cross_pass(const float (&X)[kNR][FP], const floa
             S[0] += p0;
             S[1] += p1;
             const float w0 = p0 * v.x;  // armnet.py:36 (normalisation by S is applied once, after the sum)
+            const float w1 = p1 * v.y;
+#pragma unroll
+            for (int x = 0; x < EC; ++x) {
+                acc[0][x] = fmaf(w0, e[x], acc[0][x]);
+                acc[1][x] = fmaf(w1, e[x], acc[1][x]);
+            }
+        }
+    }
+}
+
+// Fused first pass for POW_GENERAL: gates, cross product AND the Newton residual sums at the same tau, so that a
+// start which is already converged costs one sweep (2 MUFU per element) instead of a solver sweep plus a cross sweep.
+template <int FP, bool EXACT, int EC, int E_STRIDE>
+__device__ __forceinline__ void fused_first_pass(const float (&X)[kNR][FP], const float (&tau)[kNR],
+                                                 const EntmaxParams &ep, const float *eb, const float2 *vrow, int F,
+                                                 float (&acc)[kNR][EC], float (&S)[kNR], float (&S1)[kNR]) {
+#pragma unroll
+    for (int f = 0; f < FP; ++f) {
+        if (EXACT || f < F) {
+            float e[EC];
+            load_e_chunk<EC>(eb + f * E_STRIDE, e);
+            const float2 v = vrow[f];
+            const float u0 = fmaxf(X[0][f] - tau[0], 0.f);
+            const float u1 = fmaxf(X[1][f] - tau[1], 0.f);
+            const float g0 = fast_ex2(ep.qm1 * fast_lg2(u0));  // u^(q-1)
+            const float g1 = fast_ex2(ep.qm1 * fast_lg2(u1));
+            S1[0] += g0;
+            S1[1] += g1;
+            const float p0 = g0 * u0;  // u^q
+            const float p1 = g1 * u1;
+            S[0] += p0;
+            S[1] += p1;
+            const float w0 = p0 * v.x;
             const float w1 = p1 * v.y;
 #pragma unroll
             for (int x = 0; x < EC; ++x) {
@@ -387,22 +428,51 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
         // alive across the solver (and spills them) instead of re-issuing 29-cycle LDS.
         asm volatile("" ::: "memory");
 
-        // ---- thresholds (entmax.py:44-61), both rows of the pair together
+        // ---- thresholds (entmax.py:44-61) and gates*values / log-space product (armnet.py:36,87), both rows together
         float tau[kNR];
-        entmax_solve_tau<kNR, FP, EXACT>(X, F, ep, tau);
-        asm volatile("" ::: "memory");
-
-        // ---- gates, gates*values and the log-space product s = sum_f w_f e_f (armnet.py:36,87)
         float acc[kNR][EC];
 #pragma unroll
         for (int x = 0; x < EC; ++x) acc[0][x] = acc[1][x] = 0.f;
         float S[kNR] = {0.f, 0.f};
         const float2 *vrow = Vs2 + j2 * L.vstr;
-        switch (ep.mode) {
-            case POW_SOFTMAX: cross_pass<POW_SOFTMAX, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
-            case POW_LINEAR: cross_pass<POW_LINEAR, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
-            case POW_SQUARE: cross_pass<POW_SQUARE, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
-            default: cross_pass<POW_GENERAL, FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S); break;
+        bool finished = false, warm = false;
+        float mx[kNR], mean[kNR];
+        row_max_mean<FP, EXACT>(X[0], F, ep, mx[0], mean[0]);
+        row_max_mean<FP, EXACT>(X[1], F, ep, mx[1], mean[1]);
+        // near-uniform rows (random-init weights, weakly attending neurons): closed-form start, verified by the Newton
+        // residual of a fused first pass. The quick test costs nothing; the variance is only computed when it passes.
+        if (ep.mode == POW_GENERAL &&
+            __all_sync(0xffffffffu, fmaxf(mx[0] - mean[0], mx[1] - mean[1]) <= 0.2f * ep.cF)) {
+            const bool nu0 = entmax_uniform_start<FP, EXACT>(X[0], F, ep, mx[0], mean[0], tau[0]);
+            const bool nu1 = entmax_uniform_start<FP, EXACT>(X[1], F, ep, mx[1], mean[1], tau[1]);
+            if (__all_sync(0xffffffffu, nu0 && nu1)) {
+                float S1[kNR] = {0.f, 0.f};
+                fused_first_pass<FP, EXACT, EC, E_STRIDE>(X, tau, ep, opaque_ptr(eb), vrow, F, acc, S, S1);
+                asm volatile("" ::: "memory");
+                const float d0 = __fdividef(S[0] - 1.f, ep.q * S1[0]);
+                const float d1 = __fdividef(S[1] - 1.f, ep.q * S1[1]);
+                if (__all_sync(0xffffffffu, fabsf(d0) <= 1e-6f && fabsf(d1) <= 1e-6f)) {
+                    finished = true;  // |dp| <= q * 1e-6 before renormalisation: inside the parity budget
+                } else {            // keep the Newton step, continue with the regular solver
+                    tau[0] += d0;
+                    tau[1] += d1;
+                    warm = true;
+#pragma unroll
+                    for (int x = 0; x < EC; ++x) acc[0][x] = acc[1][x] = 0.f;
+                    S[0] = S[1] = 0.f;
+                }
+            }
+        }
+        if (!finished) {
+            entmax_solve_tau<kNR, FP, EXACT>(X, F, ep, mx, mean, tau, warm);
+            asm volatile("" ::: "memory");
+            const float *ebc = opaque_ptr(eb);
+            switch (ep.mode) {
+                case POW_SOFTMAX: cross_pass<POW_SOFTMAX, FP, EXACT, EC, E_STRIDE>(X, tau, ep, ebc, vrow, F, acc, S); break;
+                case POW_LINEAR: cross_pass<POW_LINEAR, FP, EXACT, EC, E_STRIDE>(X, tau, ep, ebc, vrow, F, acc, S); break;
+                case POW_SQUARE: cross_pass<POW_SQUARE, FP, EXACT, EC, E_STRIDE>(X, tau, ep, ebc, vrow, F, acc, S); break;
+                default: cross_pass<POW_GENERAL, FP, EXACT, EC, E_STRIDE>(X, tau, ep, ebc, vrow, F, acc, S); break;
+            }
         }
         // every lane is done reading the tile: hand the slot back (one arrival per unit)
         __syncwarp();
