@@ -38,25 +38,26 @@ static const FwdInstance *select_instance(int F, int E) {
     return best;
 }
 
-// Pre-contracted attention parameters in the row-pair layout the kernel reads (float2 = rows 2j, 2j+1):
-//   Mg2[j][x] = M'[x][2j..2j+1],  M'[x][r] = (alpha-1) * d_k^-0.5 * sum_y W[k,x,y] Q[k,o,y]   (r = k*O + o)
+// Pre-contracted attention parameters in the row-pair layout the kernel reads (pair j = rows 2j, 2j+1):
+//   Mg2 (floats) [j][n][x], pair stride 2*mstr floats: M'[x][2j+n] for x < E_lanes, n in {0,1}
+//       M'[x][r] = (alpha-1) * d_k^-0.5 * sum_y W[k,x,y] Q[k,o,y]   (r = k*O + o)
 //       armnet.py:33-34 'bfx,kxy,koy->bkof' * scale, contracted over y first; entmax.py:42 X = g*(alpha-1).
 //       one-head: keys = e W_lin^T then keys.Q (armnet_1h.py:30-32), i.e. W[x,y] = W_lin[y,x].
-//   Vg2[j][f] = att_values[2j..2j+1][f]                                                      (armnet.py:36)
-// Entries with x >= E, f >= F or row >= R are zero.
+//   Vg2 (float2) [j][f] = att_values[2j..2j+1][f]                                            (armnet.py:36)
+// Entries with x >= E, f >= F or row >= R (and the stride padding) are zero.
 __global__ void attn_prepare_kernel(const float *__restrict__ W, const float *__restrict__ Q,
                                     const float *__restrict__ Vals, int lin_layout, int F, int E, int D, int O, int R,
-                                    int R2, int mstr, int vstr, float scale, float am1, float *__restrict__ Mg2,
-                                    float *__restrict__ Vg2) {
+                                    int R2, int E_lanes, int mstr, int vstr, float scale, float am1,
+                                    float *__restrict__ Mg2, float *__restrict__ Vg2) {
     const int nM = R2 * mstr * 2;
     const int total = nM + R2 * vstr * 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         if (i < nM) {
-            const int half = i & 1, jx = i >> 1;
-            const int j = jx / mstr, x = jx - j * mstr;
-            const int r = 2 * j + half;
+            const int j = i / (mstr * 2), rem = i - j * (mstr * 2);
+            const int n = rem / E_lanes, x = rem - n * E_lanes;
+            const int r = 2 * j + n;
             float a = 0.f;
-            if (x < E && r < R) {
+            if (n < 2 && x < E && r < R) {
                 const int k = r / O;
                 const float *q = Q + (long long)r * D;
                 if (lin_layout) {
@@ -200,7 +201,7 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
         const int nw = atoi(f);
         if (nw >= 1 && nw <= kMaxWarps) P.NW = nw;
     }
-    P.lockstep = getenv("ARMNET_DYNAMIC") ? 0 : 1;
+    P.lockstep = getenv("ARMNET_LOCKSTEP") ? 1 : 0;  // default: units handed out dynamically
 
     // ---- TMA eligibility
     P.row_bytes = round_up(E * 4, 16);
@@ -250,7 +251,7 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
         int blocks = (total + 255) / 256;
         if (blocks > di.sm_count * 4) blocks = di.sm_count * 4;
         attn_prepare_kernel<<<blocks, 256, 0, st>>>(bilinear_w, query, att_values, w_is_linear_layout, F, E, D, O, R, R2,
-                                                     mstr, vstr, scale, P.ep.am1, Mg2, Vg2);
+                                                     E_lanes, mstr, vstr, scale, P.ep.am1, Mg2, Vg2);
         ARMNET_CUDA_TRY(cudaGetLastError());
     }
     ARMNET_CUDA_TRY(cudaFuncSetAttribute(I->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));

@@ -26,7 +26,7 @@
 //     granularity of bulk copies does not fit the shape.
 #pragma once
 
-#include "entmax.cuh"
+#include "entmax_pair.cuh"
 
 namespace armnet {
 
@@ -103,52 +103,42 @@ struct SmemLayout {
     }
 };
 
-// Returns p unchanged but opaque to the optimiser. Each phase (logits / fused first pass / cross pass) re-reads the
-// e tile from shared memory through its own opaque pointer; otherwise nvcc value-numbers the loads across phases,
-// keeps F*E values alive through the solver and spills them to local memory.
-__device__ __forceinline__ const float *opaque_ptr(const float *p) {
-    asm volatile("" : "+l"(p));
-    return p;
-}
+// Phase boundary (logits | fused first pass | cross pass).  Each phase re-reads the e tile from shared memory.  Without
+// a real fence between them nvcc/ptxas value-number the LDS across phases, keep F*E values alive through the solver
+// and spill them to local memory (kilobytes of stack); a CTA-scope fence costs a few dozen cycles per unit.
+__device__ __forceinline__ void phase_fence() { __threadfence_block(); }
 
-// EC consecutive floats of one e row, as float4s plus a float2 tail (EC even).
+// EC consecutive floats of one e row as EC/2 register pairs (x, x+1): float4 loads plus a float2 tail (EC even).
 template <int EC>
-__device__ __forceinline__ void load_e_chunk(const float *src, float (&e)[EC]) {
+__device__ __forceinline__ void load_e_chunk(const float *src, float2 (&e)[EC / 2]) {
 #pragma unroll
     for (int j = 0; j < EC / 4; ++j) {
         const float4 t = reinterpret_cast<const float4 *>(src)[j];
-        e[4 * j + 0] = t.x;
-        e[4 * j + 1] = t.y;
-        e[4 * j + 2] = t.z;
-        e[4 * j + 3] = t.w;
+        e[2 * j + 0] = make_float2(t.x, t.y);
+        e[2 * j + 1] = make_float2(t.z, t.w);
     }
-    if (EC % 4 == 2) {
-        const float2 t = *reinterpret_cast<const float2 *>(src + (EC / 4) * 4);
-        e[EC - 2] = t.x;
-        e[EC - 1] = t.y;
-    }
+    if (EC % 4 == 2) e[EC / 2 - 1] = *reinterpret_cast<const float2 *>(src + (EC / 4) * 4);
 }
 
+// Final pass: gates of both rows at the solved tau, gates*values (armnet.py:36) and the log-space product
+// s[x] += w_f e[f,x] (armnet.py:87).  acc[n][x/2] holds (s[x], s[x+1]) of row n: one FFMA2 per two embedding lanes.
 template <int MODE, int FP, bool EXACT, int EC, int E_STRIDE>
-__device__ __forceinline__ void cross_pass(const float (&X)[kNR][FP], const float (&tau)[kNR], const EntmaxParams &ep,
-                                           const float *eb, const float2 *vrow, int F, float (&acc)[kNR][EC],
-                                           float (&S)[kNR]) {
+__device__ __forceinline__ void cross_pass(const float2 (&X)[FP], float2 tau, const EntmaxParams &ep, const float *eb,
+                                           const float2 *vrow, int F, float2 (&acc)[kNR][EC / 2], float2 &S) {
+    const float2 nt = make_float2(-tau.x, -tau.y);
 #pragma unroll
     for (int f = 0; f < FP; ++f) {
         if (EXACT || f < F) {
-            float e[EC];
+            float2 e[EC / 2];
             load_e_chunk<EC>(eb + f * E_STRIDE, e);
-            const float2 v = vrow[f];
-            const float p0 = gate_unnorm<MODE>(X[0][f], tau[0], ep);
-            const float p1 = gate_unnorm<MODE>(X[1][f], tau[1], ep);
-            S[0] += p0;
-            S[1] += p1;
-            const float w0 = p0 * v.x;  // armnet.py:36 (normalisation by S is applied once, after the sum)
-            const float w1 = p1 * v.y;
+            const float2 p = gate_unnorm2<MODE>(X[f], nt, ep);
+            S = fadd2(S, p);
+            const float2 w = fmul2(p, vrow[f]);  // normalisation by S is applied once, after the sum
+            const float2 w0 = splat2(w.x), w1 = splat2(w.y);
 #pragma unroll
-            for (int x = 0; x < EC; ++x) {
-                acc[0][x] = fmaf(w0, e[x], acc[0][x]);
-                acc[1][x] = fmaf(w1, e[x], acc[1][x]);
+            for (int x = 0; x < EC / 2; ++x) {
+                acc[0][x] = ffma2(w0, e[x], acc[0][x]);
+                acc[1][x] = ffma2(w1, e[x], acc[1][x]);
             }
         }
     }
@@ -157,31 +147,28 @@ __device__ __forceinline__ void cross_pass(const float (&X)[kNR][FP], const floa
 // Fused first pass for POW_GENERAL: gates, cross product AND the Newton residual sums at the same tau, so that a
 // start which is already converged costs one sweep (2 MUFU per element) instead of a solver sweep plus a cross sweep.
 template <int FP, bool EXACT, int EC, int E_STRIDE>
-__device__ __forceinline__ void fused_first_pass(const float (&X)[kNR][FP], const float (&tau)[kNR],
-                                                 const EntmaxParams &ep, const float *eb, const float2 *vrow, int F,
-                                                 float (&acc)[kNR][EC], float (&S)[kNR], float (&S1)[kNR]) {
+__device__ __forceinline__ void fused_first_pass(const float2 (&X)[FP], float2 tau, const EntmaxParams &ep,
+                                                 const float *eb, const float2 *vrow, int F,
+                                                 float2 (&acc)[kNR][EC / 2], float2 &S, float2 &S1) {
+    const float2 nt = make_float2(-tau.x, -tau.y);
+    const float2 qm1 = splat2(ep.qm1);
 #pragma unroll
     for (int f = 0; f < FP; ++f) {
         if (EXACT || f < F) {
-            float e[EC];
+            float2 e[EC / 2];
             load_e_chunk<EC>(eb + f * E_STRIDE, e);
-            const float2 v = vrow[f];
-            const float u0 = fmaxf(X[0][f] - tau[0], 0.f);
-            const float u1 = fmaxf(X[1][f] - tau[1], 0.f);
-            const float g0 = fast_ex2(ep.qm1 * fast_lg2(u0));  // u^(q-1)
-            const float g1 = fast_ex2(ep.qm1 * fast_lg2(u1));
-            S1[0] += g0;
-            S1[1] += g1;
-            const float p0 = g0 * u0;  // u^q
-            const float p1 = g1 * u1;
-            S[0] += p0;
-            S[1] += p1;
-            const float w0 = p0 * v.x;
-            const float w1 = p1 * v.y;
+            const float2 u = relu2(fadd2(X[f], nt));
+            const float2 t = fmul2(make_float2(fast_lg2(u.x), fast_lg2(u.y)), qm1);
+            const float2 g = make_float2(fast_ex2(t.x), fast_ex2(t.y));  // u^(q-1)
+            S1 = fadd2(S1, g);
+            const float2 p = fmul2(g, u);  // u^q
+            S = fadd2(S, p);
+            const float2 w = fmul2(p, vrow[f]);
+            const float2 w0 = splat2(w.x), w1 = splat2(w.y);
 #pragma unroll
-            for (int x = 0; x < EC; ++x) {
-                acc[0][x] = fmaf(w0, e[x], acc[0][x]);
-                acc[1][x] = fmaf(w1, e[x], acc[1][x]);
+            for (int x = 0; x < EC / 2; ++x) {
+                acc[0][x] = ffma2(w0, e[x], acc[0][x]);
+                acc[1][x] = ffma2(w1, e[x], acc[1][x]);
             }
         }
     }
@@ -382,36 +369,40 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
         const int r0 = 2 * j2;
         const bool has1 = (r0 + 1 < R);             // odd R: the last pair's second row is a dummy
         const long long grow = (b0 + bl) * R + r0;  // global index of the pair's first row
-        const float *eb = es + slot * L.slot_floats + bl * F * E_STRIDE + c * EC;
+        const int e_off = slot * L.slot_floats + bl * F * E_STRIDE + c * EC;
+        const float *eb = es + e_off;
 
-        // ---- X = (alpha-1) * g = e . M' (armnet.py:33-34 and entmax.py:42; both scalings are folded into M')
-        float X[kNR][FP];
+        // ---- X = (alpha-1) * g = e . M' (armnet.py:33-34 and entmax.py:42; both scalings are folded into M').
+        // X[f] = (row0, row1); the dot product over x runs as EC/2 FFMA2 on (even, odd) partial sums.
+        float2 X[FP];
         {
-            float2 Mr[EC];
-            const float2 *mrow = Ms2 + j2 * L.mstr + c * EC;
+            float2 Mr[kNR][EC / 2];
+            const float2 *mrow = Ms2 + j2 * L.mstr + (c * EC) / 2;
 #pragma unroll
-            for (int x = 0; x < EC; ++x) Mr[x] = mrow[x];
+            for (int x = 0; x < EC / 2; ++x) {
+                Mr[0][x] = mrow[x];
+                Mr[1][x] = mrow[E_LANES / 2 + x];
+            }
 #pragma unroll
             for (int f = 0; f < FP; ++f) {
                 if (EXACT || f < F) {
-                    float e[EC];
+                    float2 e[EC / 2];
                     load_e_chunk<EC>(eb + f * E_STRIDE, e);
-                    float a0 = 0.f, a1 = 0.f;
+                    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int x = 0; x < EC; ++x) {
-                        a0 = fmaf(e[x], Mr[x].x, a0);
-                        a1 = fmaf(e[x], Mr[x].y, a1);
+                    for (int x = 0; x < EC / 2; ++x) {
+                        a0 = ffma2(e[x], Mr[0][x], a0);
+                        a1 = ffma2(e[x], Mr[1][x], a1);
                     }
+                    float s0 = a0.x + a0.y, s1 = a1.x + a1.y;
 #pragma unroll
                     for (int m = 1; m < ES; m <<= 1) {
-                        a0 += __shfl_xor_sync(0xffffffffu, a0, m);
-                        a1 += __shfl_xor_sync(0xffffffffu, a1, m);
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, m);
                     }
-                    X[0][f] = a0;
-                    X[1][f] = a1;
+                    X[f] = make_float2(s0, s1);
                 } else {
-                    X[0][f] = neg_inf();
-                    X[1][f] = neg_inf();
+                    X[f] = make_float2(neg_inf(), neg_inf());
                 }
             }
         }
@@ -419,54 +410,48 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
 #pragma unroll
             for (int f = 0; f < FP; ++f) {
                 if (EXACT || f < F) {
-                    P.out_g[grow * F + f] = X[0][f] * P.g_unscale;
-                    if (has1) P.out_g[(grow + 1) * F + f] = X[1][f] * P.g_unscale;
+                    P.out_g[grow * F + f] = X[f].x * P.g_unscale;
+                    if (has1) P.out_g[(grow + 1) * F + f] = X[f].y * P.g_unscale;
                 }
             }
         }
-        // The cross pass re-reads e from shared memory; without this compiler barrier nvcc keeps all loaded e values
-        // alive across the solver (and spills them) instead of re-issuing 29-cycle LDS.
-        asm volatile("" ::: "memory");
+        phase_fence();
 
         // ---- thresholds (entmax.py:44-61) and gates*values / log-space product (armnet.py:36,87), both rows together
-        float tau[kNR];
-        float acc[kNR][EC];
+        float2 tau;
+        float2 acc[kNR][EC / 2];
 #pragma unroll
-        for (int x = 0; x < EC; ++x) acc[0][x] = acc[1][x] = 0.f;
-        float S[kNR] = {0.f, 0.f};
+        for (int x = 0; x < EC / 2; ++x) acc[0][x] = acc[1][x] = make_float2(0.f, 0.f);
+        float2 S = make_float2(0.f, 0.f);
         const float2 *vrow = Vs2 + j2 * L.vstr;
         bool finished = false, warm = false;
-        float mx[kNR], mean[kNR];
-        row_max_mean<FP, EXACT>(X[0], F, ep, mx[0], mean[0]);
-        row_max_mean<FP, EXACT>(X[1], F, ep, mx[1], mean[1]);
+        float2 mx, mean;
+        row_max_mean2<FP, EXACT>(X, F, ep, mx, mean);
         // near-uniform rows (random-init weights, weakly attending neurons): closed-form start, verified by the Newton
         // residual of a fused first pass. The quick test costs nothing; the variance is only computed when it passes.
         if (ep.mode == POW_GENERAL &&
-            __all_sync(0xffffffffu, fmaxf(mx[0] - mean[0], mx[1] - mean[1]) <= 0.2f * ep.cF)) {
-            const bool nu0 = entmax_uniform_start<FP, EXACT>(X[0], F, ep, mx[0], mean[0], tau[0]);
-            const bool nu1 = entmax_uniform_start<FP, EXACT>(X[1], F, ep, mx[1], mean[1], tau[1]);
-            if (__all_sync(0xffffffffu, nu0 && nu1)) {
-                float S1[kNR] = {0.f, 0.f};
-                fused_first_pass<FP, EXACT, EC, E_STRIDE>(X, tau, ep, opaque_ptr(eb), vrow, F, acc, S, S1);
-                asm volatile("" ::: "memory");
-                const float d0 = __fdividef(S[0] - 1.f, ep.q * S1[0]);
-                const float d1 = __fdividef(S[1] - 1.f, ep.q * S1[1]);
-                if (__all_sync(0xffffffffu, fabsf(d0) <= 1e-6f && fabsf(d1) <= 1e-6f)) {
+            __all_sync(0xffffffffu, fmaxf(mx.x - mean.x, mx.y - mean.y) <= 0.2f * ep.cF)) {
+            if (__all_sync(0xffffffffu, entmax_uniform_start2<FP, EXACT>(X, F, ep, mx, mean, tau))) {
+                float2 S1 = make_float2(0.f, 0.f);
+                fused_first_pass<FP, EXACT, EC, E_STRIDE>(X, tau, ep, eb, vrow, F, acc, S, S1);
+                const float d0 = __fdividef(S.x - 1.f, ep.q * S1.x);
+                const float d1 = __fdividef(S.y - 1.f, ep.q * S1.y);
+                if (__all_sync(0xffffffffu, fmaxf(fabsf(d0), fabsf(d1)) <= 1e-6f)) {
                     finished = true;  // |dp| <= q * 1e-6 before renormalisation: inside the parity budget
                 } else {            // keep the Newton step, continue with the regular solver
-                    tau[0] += d0;
-                    tau[1] += d1;
+                    tau.x += d0;
+                    tau.y += d1;
                     warm = true;
 #pragma unroll
-                    for (int x = 0; x < EC; ++x) acc[0][x] = acc[1][x] = 0.f;
-                    S[0] = S[1] = 0.f;
+                    for (int x = 0; x < EC / 2; ++x) acc[0][x] = acc[1][x] = make_float2(0.f, 0.f);
+                    S = make_float2(0.f, 0.f);
                 }
             }
         }
         if (!finished) {
-            entmax_solve_tau<kNR, FP, EXACT>(X, F, ep, mx, mean, tau, warm);
-            asm volatile("" ::: "memory");
-            const float *ebc = opaque_ptr(eb);
+            entmax_solve_tau2<FP, EXACT>(X, F, ep, mx, mean, tau, warm);
+            phase_fence();
+            const float *ebc = eb;
             switch (ep.mode) {
                 case POW_SOFTMAX: cross_pass<POW_SOFTMAX, FP, EXACT, EC, E_STRIDE>(X, tau, ep, ebc, vrow, F, acc, S); break;
                 case POW_LINEAR: cross_pass<POW_LINEAR, FP, EXACT, EC, E_STRIDE>(X, tau, ep, ebc, vrow, F, acc, S); break;
@@ -478,48 +463,54 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[slot]);
 
-        const float inv0 = __frcp_rn(S[0]);  // entmax.py:63-64 renormalisation
-        const float inv1 = __frcp_rn(S[1]);
+        const float inv0 = __frcp_rn(S.x);  // entmax.py:63-64 renormalisation
+        const float inv1 = __frcp_rn(S.y);
 
         if (valid && c == 0 && (P.out_tau != nullptr || P.out_p != nullptr)) {
             if (P.out_tau != nullptr) {
-                P.out_tau[2 * grow + 0] = tau[0];
-                P.out_tau[2 * grow + 1] = S[0];
+                P.out_tau[2 * grow + 0] = tau.x;
+                P.out_tau[2 * grow + 1] = S.x;
                 if (has1) {
-                    P.out_tau[2 * grow + 2] = tau[1];
-                    P.out_tau[2 * grow + 3] = S[1];
+                    P.out_tau[2 * grow + 2] = tau.y;
+                    P.out_tau[2 * grow + 3] = S.y;
                 }
             }
             if (P.out_p != nullptr) {
+                const float2 nt = make_float2(-tau.x, -tau.y);
 #pragma unroll
                 for (int f = 0; f < FP; ++f) {  // static indices only: X must stay in registers
                     if (EXACT || f < F) {
-                        P.out_p[grow * F + f] = __fdiv_rn(gate_unnorm_rt(X[0][f], tau[0], ep), S[0]);
-                        if (has1) P.out_p[(grow + 1) * F + f] = __fdiv_rn(gate_unnorm_rt(X[1][f], tau[1], ep), S[1]);
+                        const float2 pu = gate_unnorm2_rt(X[f], nt, ep);
+                        P.out_p[grow * F + f] = __fdiv_rn(pu.x, S.x);
+                        if (has1) P.out_p[(grow + 1) * F + f] = __fdiv_rn(pu.y, S.y);
                     }
                 }
             }
         }
+        // s = acc / S, z = exp(s) (armnet.py:86) [then eval-mode arm_bn, armnet.py:89]
+        float z[kNR][EC];
 #pragma unroll
-        for (int x = 0; x < EC; ++x) {
-            acc[0][x] *= inv0;
-            acc[1][x] *= inv1;
+        for (int x = 0; x < EC / 2; ++x) {
+            const float2 s0 = fmul2(acc[0][x], splat2(inv0));
+            const float2 s1 = fmul2(acc[1][x], splat2(inv1));
+            z[0][2 * x] = s0.x;
+            z[0][2 * x + 1] = s0.y;
+            z[1][2 * x] = s1.x;
+            z[1][2 * x + 1] = s1.y;
         }
         if (P.out_s != nullptr && valid) {
 #pragma unroll
             for (int x = 0; x < EC; ++x) {
                 if (c * EC + x < E) {
-                    P.out_s[grow * E + c * EC + x] = acc[0][x];
-                    if (has1) P.out_s[(grow + 1) * E + c * EC + x] = acc[1][x];
+                    P.out_s[grow * E + c * EC + x] = z[0][x];
+                    if (has1) P.out_s[(grow + 1) * E + c * EC + x] = z[1][x];
                 }
             }
         }
-
-        // ---- z = exp(s) (armnet.py:86) [then eval-mode arm_bn, armnet.py:89], written as [b][r][0:E]
 #pragma unroll
         for (int x = 0; x < EC; ++x) {
-            acc[0][x] = expf(acc[0][x]);
-            acc[1][x] = expf(acc[1][x]);
+            z[0][x] = expf(z[0][x]);
+            z[1][x] = expf(z[1][x]);
         }
         if (P.post_scale != nullptr) {
             const int r1 = has1 ? r0 + 1 : r0;
@@ -527,8 +518,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
             const float m1 = __ldg(P.post_mean + r1), a1 = __ldg(P.post_scale + r1), h1 = __ldg(P.post_shift + r1);
 #pragma unroll
             for (int x = 0; x < EC; ++x) {
-                acc[0][x] = fmaf(acc[0][x] - m0, a0, h0);
-                acc[1][x] = fmaf(acc[1][x] - m1, a1, h1);
+                z[0][x] = fmaf(z[0][x] - m0, a0, h0);
+                z[1][x] = fmaf(z[1][x] - m1, a1, h1);
             }
         }
         // the unit's rows [2*p_first, 2*min(p_first+PPW, n_pairs)) of the tile are contiguous in out_z when R is even
@@ -543,8 +534,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
 #pragma unroll
                 for (int x = 0; x < EC; ++x) {
                     if (c * EC + x < E) {
-                        ost[x] = acc[0][x];
-                        ost[E + x] = acc[1][x];
+                        ost[x] = z[0][x];
+                        ost[E + x] = z[1][x];
                     }
                 }
             }
@@ -559,8 +550,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
 #pragma unroll
             for (int x = 0; x < EC; ++x) {
                 if (c * EC + x < E) {
-                    dst[x] = acc[0][x];
-                    if (has1) dst[E + x] = acc[1][x];
+                    dst[x] = z[0][x];
+                    if (has1) dst[E + x] = z[1][x];
                 }
             }
         }
