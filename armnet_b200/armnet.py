@@ -80,6 +80,7 @@ class ARMNetModel(nn.Module):
         self.validate_ids = False    # synchronising id-range check after each forward (reference: IndexError)
         self.solver = ops.SOLVER_AUTO
         self.fuse_bn = True          # eval mode: apply arm_bn in the kernel epilogue
+        self.fused_backward = True   # training: fused backward kernel (else unfused autograd stages)
         self._shadow = _PaddedTable()
         self._err_flag = None
         self._bn_key = None
@@ -119,7 +120,17 @@ class ARMNetModel(nn.Module):
         return (z, extra) if want else z
 
     def _interaction_autograd(self, x):
-        """Same stages with autograd recording (training): CUDA gather + cuBLAS einsums + CUDA entmax fwd/bwd."""
+        """Training: fused forward + fused backward kernels (ops.fused_interaction) when a backward instance exists
+        for (nfield, nemb); otherwise the same stages unfused under autograd (CUDA gather + cuBLAS einsums + CUDA
+        entmax forward/backward)."""
+        table = self.embedding.embedding.weight
+        if self.fused_backward and ops.fused_bwd_supported(x['id'].shape[1], table.shape[1]):
+            W, Q, Vv = self._attn_weights()
+            return ops.fused_interaction(table, W, Q, Vv, x['id'], x['value'], self.alpha, one_head=self.one_head,
+                                         solver=self.solver)
+        return self._interaction_unfused(x)
+
+    def _interaction_unfused(self, x):
         x['value'].clamp_(0.001, 1.)
         e = self.embedding(x)
         w = self.attn_layer(e)

@@ -57,6 +57,7 @@ class ARMNetModel(_MultiHead):
         self.validate_ids = False
         self.solver = ops.SOLVER_AUTO
         self.fuse_bn = True
+        self.fused_backward = True
         self._shadow = _PaddedTable()
         self._err_flag = None
         self._bn_key = None
@@ -65,7 +66,7 @@ class ARMNetModel(_MultiHead):
         a = self.attn_layer
         return a.bilinear_w.weight, a.query, a.values
 
-    def _interaction_autograd(self, x):
+    def _interaction_unfused(self, x):
         x['value'].clamp_(1e-3, 1.)
         e = self.embedding(x)
         w = self.attn_layer(e)

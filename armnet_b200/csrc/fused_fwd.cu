@@ -2,6 +2,7 @@
 // pre-contraction).  Kernel: fused_fwd.cuh.  Instances: fused_fwd_inst_*.cu.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "fused_fwd.cuh"
 
@@ -16,13 +17,19 @@ extern const FwdInstance kFwdInstancesC[];
 extern const int kNumFwdInstancesC;
 extern const FwdInstance kFwdInstancesD[];
 extern const int kNumFwdInstancesD;
+extern const FwdInstance kFwdInstancesE[];
+extern const int kNumFwdInstancesE;
+extern const FwdInstance kFwdInstancesF[];
+extern const int kNumFwdInstancesF;
 
 static const FwdInstance *select_instance(int F, int E) {
-    const FwdInstance *tabs[] = {kFwdInstancesA, kFwdInstancesB, kFwdInstancesC, kFwdInstancesD};
-    const int ns[] = {kNumFwdInstancesA, kNumFwdInstancesB, kNumFwdInstancesC, kNumFwdInstancesD};
+    const FwdInstance *tabs[] = {kFwdInstancesA, kFwdInstancesB, kFwdInstancesC,
+                                 kFwdInstancesD, kFwdInstancesE, kFwdInstancesF};
+    const int ns[] = {kNumFwdInstancesA, kNumFwdInstancesB, kNumFwdInstancesC,
+                      kNumFwdInstancesD, kNumFwdInstancesE, kNumFwdInstancesF};
     const FwdInstance *best = nullptr;
     long best_cost = 0;
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < 6; ++t) {
         for (int i = 0; i < ns[t]; ++i) {
             const FwdInstance &I = tabs[t][i];
             if (I.exact ? (I.FP != F) : (I.FP < F)) continue;
@@ -93,41 +100,54 @@ extern "C" size_t armnet_fused_workspace_bytes(int F, int E, int K, int O) {
     return (R2 * mstr * 8 + 15) / 16 * 16 + (R2 * vstr * 8 + 15) / 16 * 16;  // bulk-copy granularity
 }
 
-extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V,
-                                    int64_t ld, const float *bilinear_w, const float *query, const float *att_values,
-                                    int w_is_linear_layout, float alpha, int solver, int n_iter, int64_t B, int F,
-                                    int E, int D, int K, int O, int clamp, float clamp_lo, float clamp_hi,
-                                    int clamp_inplace, const float *post_mean, const float *post_scale,
-                                    const float *post_shift, float *out_z, float *out_tau, float *out_p, float *out_g,
-                                    float *out_s, void *workspace, int *err_flag, void *stream) {
-    using namespace armnet;
+namespace armnet {
+
+struct BwdArgs {
+    const float *z, *dz, *tau;
+    float *wA, *gA, *dV, *dM;
+};
+
+// Shared by the forward and backward entries: validation, instance selection, geometry, shared-memory budget,
+// parameter pre-contraction and the launch.
+static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, int ids_i32, float *values,
+                        const float *table, int64_t V, int64_t ld, const float *bilinear_w, const float *query,
+                        const float *att_values, int w_is_linear_layout, float alpha, int solver, int n_iter, int64_t B,
+                        int F, int E, int D, int K, int O, int clamp, float clamp_lo, float clamp_hi, int clamp_inplace,
+                        const float *post_mean, const float *post_scale, const float *post_shift, float *out_z,
+                        float *out_tau, float *out_p, float *out_g, float *out_s, void *workspace, int *err_flag,
+                        void *stream) {
     note_launches(0);
     if (B == 0) return ARMNET_OK;  // empty batch: nothing to read or write (tensors may have null data pointers)
-    if (!ids || !values || !table || !bilinear_w || !query || !att_values || !out_z || !workspace) {
-        set_error("fused_fwd: null pointer");
+    if (!ids || !values || !table || !bilinear_w || !query || !att_values || !workspace || (!bwd && !out_z) ||
+        (bwd && (!bwd->z || !bwd->dz || !bwd->tau || !bwd->wA || !bwd->gA || !bwd->dV || !bwd->dM))) {
+        set_error("%s: null pointer", who);
         return ARMNET_ERR_NULL;
     }
     if (V <= 0 || B < 0 || F <= 0 || E <= 0 || D <= 0 || K <= 0 || O <= 0 || ld < E ||
         (w_is_linear_layout && K != 1) || B * (int64_t)K * O > (int64_t)1 << 40) {
-        set_error("fused_fwd: bad shape V=%lld ld=%lld B=%lld F=%d E=%d D=%d K=%d O=%d", (long long)V, (long long)ld,
+        set_error("%s: bad shape V=%lld ld=%lld B=%lld F=%d E=%d D=%d K=%d O=%d", who, (long long)V, (long long)ld,
                   (long long)B, F, E, D, K, O);
         return ARMNET_ERR_SHAPE;
     }
     if ((uintptr_t)workspace % 16 || (uintptr_t)table % 4 || (uintptr_t)out_z % 4 || (uintptr_t)values % 4 ||
         (uintptr_t)ids % (ids_i32 ? 4 : 8)) {
-        set_error("fused_fwd: misaligned pointer");
+        set_error("%s: misaligned pointer", who);
         return ARMNET_ERR_ALIGN;
     }
     if (V > 0x7fffffffLL) {
-        set_error("fused_fwd: nfeat=%lld exceeds the 2^31-1 rows the kernel indexes", (long long)V);
+        set_error("%s: nfeat=%lld exceeds the 2^31-1 rows the kernel indexes", who, (long long)V);
         return ARMNET_ERR_UNSUPPORTED;
     }
     const FwdInstance *I = select_instance(F, E);
-    if (!I) {
-        set_error("fused_fwd: no compiled kernel instance for F=%d E=%d (F <= 64, E <= 128 in this build)", F, E);
+    if (!I || (bwd && !I->kernel_bwd)) {
+        set_error("%s: no compiled kernel instance for F=%d E=%d (forward: F <= 64, E <= 128; backward: E <= 16 and "
+                  "the BASELINE shapes in this build)", who, F, E);
         return ARMNET_ERR_UNSUPPORTED;
     }
+    const void *kernel = bwd ? I->kernel_bwd : I->kernel;
+    const int max_warps = bwd ? kBwdWarps : kMaxWarps;
     FwdParams P;
+    memset(&P, 0, sizeof(P));
     int rc = make_entmax_params(alpha, F, solver, n_iter, &P.ep);
     if (rc != ARMNET_OK) return rc;
     DeviceInfo di;
@@ -143,7 +163,7 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     float *Mg2 = (float *)workspace;
     float *Vg2 = Mg2 + ((size_t)R2 * mstr * 8 + 15) / 16 * 4;  // 16-byte padded M table, then V
     if ((post_scale != nullptr) != (post_mean != nullptr) || (post_scale != nullptr) != (post_shift != nullptr)) {
-        set_error("fused_fwd: post_mean/post_scale/post_shift must be given together");
+        set_error("%s: post_mean/post_scale/post_shift must be given together", who);
         return ARMNET_ERR_NULL;
     }
 
@@ -160,6 +180,15 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     P.out_p = out_p;
     P.out_g = out_g;
     P.out_s = out_s;
+    if (bwd) {
+        P.in_z = bwd->z;
+        P.in_dz = bwd->dz;
+        P.in_tau = bwd->tau;
+        P.out_wA = bwd->wA;
+        P.out_gA = bwd->gA;
+        P.acc_dV = bwd->dV;
+        P.acc_dM = bwd->dM;
+    }
     P.err_flag = err_flag;
     P.V = V;
     P.ld = ld;
@@ -190,16 +219,16 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     }
     const long long n_tiles = (B + P.SPG - 1) / P.SPG;
     if (n_tiles > 0x7fffffffLL / P.UPG) {
-        set_error("fused_fwd: batch too large");
+        set_error("%s: batch too large", who);
         return ARMNET_ERR_SHAPE;
     }
     P.n_tiles = (int)n_tiles;
     const unsigned grid = (unsigned)(n_tiles < di.sm_count ? n_tiles : di.sm_count);
     const long long units_per_cta = (n_tiles + grid - 1) / grid * P.UPG;
-    P.NW = (int)(units_per_cta < kMaxWarps ? units_per_cta : kMaxWarps);
+    P.NW = (int)(units_per_cta < max_warps ? units_per_cta : max_warps);
     if (const char *f = getenv("ARMNET_FORCE_NW")) {  // tuning experiments only
         const int nw = atoi(f);
-        if (nw >= 1 && nw <= kMaxWarps) P.NW = nw;
+        if (nw >= 1 && nw <= max_warps) P.NW = nw;
     }
     P.lockstep = getenv("ARMNET_LOCKSTEP") ? 1 : 0;  // default: units handed out dynamically
 
@@ -209,7 +238,7 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     if (getenv("ARMNET_NO_TMA_GATHER")) P.tma_gather = 0;
     // a unit's output rows are contiguous when pairs never straddle samples (R even); 16-byte size/alignment of each
     // bulk store is re-checked per unit in the kernel
-    P.tma_store = (getenv("ARMNET_NO_TMA_STORE") == nullptr && R % 2 == 0 && (uintptr_t)out_z % 16 == 0) ? 1 : 0;
+    P.tma_store = (!bwd && getenv("ARMNET_NO_TMA_STORE") == nullptr && R % 2 == 0 && (uintptr_t)out_z % 16 == 0) ? 1 : 0;
 
     // ---- shared-memory budget: ids/values of an epoch of tiles are preloaded; the rest of the space becomes gather
     // slots (the deeper the ring, the further ahead the TMA gathers run)
@@ -222,7 +251,7 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     int best_slots = 0;
     for (int ns = kMaxSlots; ns >= in_flight + 2; --ns) {
         P.n_slots = ns;
-        const SmemLayout Lt(I->FP, E_lanes, E_stride, ES, P);
+        const SmemLayout Lt(I->FP, E_lanes, E_stride, ES, P, bwd != nullptr);
         if (Lt.total <= di.smem_optin) {
             best_slots = ns;
             break;
@@ -230,8 +259,8 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
     }
     if (best_slots == 0) {
         P.n_slots = in_flight + 2;
-        const SmemLayout Lt(I->FP, E_lanes, E_stride, ES, P);
-        set_error("fused_fwd: F=%d E=%d K*O=%d needs %d bytes of shared memory per CTA (limit %d)", F, E, R, Lt.total,
+        const SmemLayout Lt(I->FP, E_lanes, E_stride, ES, P, bwd != nullptr);
+        set_error("%s: F=%d E=%d K*O=%d needs %d bytes of shared memory per CTA (limit %d)", who, F, E, R, Lt.total,
                   di.smem_optin);
         return ARMNET_ERR_UNSUPPORTED;
     }
@@ -243,7 +272,7 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
         const int lk = atoi(f);
         if (lk >= 1 && lk <= P.look) P.look = lk;
     }
-    const SmemLayout L(I->FP, E_lanes, E_stride, ES, P);
+    const SmemLayout L(I->FP, E_lanes, E_stride, ES, P, bwd != nullptr);
 
     cudaStream_t st = (cudaStream_t)stream;
     {
@@ -254,9 +283,42 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
                                                      E_lanes, mstr, vstr, scale, P.ep.am1, Mg2, Vg2);
         ARMNET_CUDA_TRY(cudaGetLastError());
     }
-    ARMNET_CUDA_TRY(cudaFuncSetAttribute(I->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
+    ARMNET_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
     void *args[] = {(void *)&P};
-    ARMNET_CUDA_TRY(cudaLaunchKernel(I->kernel, dim3(grid), dim3(P.NW * 32), args, (size_t)L.total, st));
+    ARMNET_CUDA_TRY(cudaLaunchKernel(kernel, dim3(grid), dim3(P.NW * 32), args, (size_t)L.total, st));
     note_launches(2);
     return ARMNET_OK;
+}
+
+}  // namespace armnet
+
+extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V,
+                                    int64_t ld, const float *bilinear_w, const float *query, const float *att_values,
+                                    int w_is_linear_layout, float alpha, int solver, int n_iter, int64_t B, int F,
+                                    int E, int D, int K, int O, int clamp, float clamp_lo, float clamp_hi,
+                                    int clamp_inplace, const float *post_mean, const float *post_scale,
+                                    const float *post_shift, float *out_z, float *out_tau, float *out_p, float *out_g,
+                                    float *out_s, void *workspace, int *err_flag, void *stream) {
+    return armnet::launch_fused("fused_fwd", nullptr, ids, ids_i32, values, table, V, ld, bilinear_w, query, att_values,
+                                w_is_linear_layout, alpha, solver, n_iter, B, F, E, D, K, O, clamp, clamp_lo, clamp_hi,
+                                clamp_inplace, post_mean, post_scale, post_shift, out_z, out_tau, out_p, out_g, out_s,
+                                workspace, err_flag, stream);
+}
+
+extern "C" int armnet_fused_bwd_supported(int F, int E) {
+    const armnet::FwdInstance *I = armnet::select_instance(F, E);
+    return (I && I->kernel_bwd) ? 1 : 0;
+}
+
+extern "C" int armnet_fused_bwd_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V,
+                                    int64_t ld, const float *bilinear_w, const float *query, const float *att_values,
+                                    int w_is_linear_layout, float alpha, int64_t B, int F, int E, int D, int K, int O,
+                                    const float *z, const float *dz, const float *tau, float *out_w, float *out_dg,
+                                    float *acc_dvalues, float *acc_dm, void *workspace, int *err_flag, void *stream) {
+    armnet::BwdArgs b = {z, dz, tau, out_w, out_dg, acc_dvalues, acc_dm};
+    // values were clamped by the forward; the solver is not used (tau is an input)
+    return armnet::launch_fused("fused_bwd", &b, ids, ids_i32, values, table, V, ld, bilinear_w, query, att_values,
+                                w_is_linear_layout, alpha, ARMNET_SOLVER_AUTO, 50, B, F, E, D, K, O, 0, 0.f, 0.f, 0,
+                                nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, workspace,
+                                err_flag, stream);
 }

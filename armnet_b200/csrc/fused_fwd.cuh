@@ -37,6 +37,7 @@ constexpr int kMaxWarps = ARMNET_MAX_WARPS;
 constexpr int kMaxThreads = kMaxWarps * 32;
 constexpr int kMaxSlots = 24;
 constexpr int kNR = 2;    // rows per thread
+constexpr int kBwdWarps = 8;  // backward keeps two F-long register arrays: 8 warps -> 255 registers per thread
 
 struct FwdParams {
     const void *ids;
@@ -52,6 +53,14 @@ struct FwdParams {
     float *out_p;             // [B][R][F] or null
     float *out_g;             // [B][R][F] or null
     float *out_s;             // [B][R][E] or null
+    // backward (BWD kernel): inputs saved by the forward, per-row outputs, batch-accumulated parameter gradients
+    const float *in_z;        // [B][R][E]  forward output (without the arm_bn epilogue)
+    const float *in_dz;       // [B][R][E]  gradient w.r.t. z
+    const float *in_tau;      // [B][R][2]  (tau, sum of unnormalised gates) saved by the forward
+    float *out_wA;            // [B][F][R]  w = p * values                       (r fastest: coalesced, bmm-ready)
+    float *out_gA;            // [B][F][R]  dg = gradient w.r.t. the logits g
+    float *acc_dV;            // [R][F]     += p * dw  over the batch (caller zeroes)
+    float *acc_dM;            // [R][E]     += sum_f dg_f e_f over the batch (caller zeroes)
     int *err_flag;
     long long V, ld, B;
     int F, E, R, R2;
@@ -84,7 +93,10 @@ struct SmemLayout {
     int rows_pad;      // ids / values entries per tile
     int out_floats;    // floats per warp staging buffer
     __host__ __device__ static int up(int x, int a) { return (x + a - 1) / a * a; }
-    __host__ __device__ SmemLayout(int FP, int E_lanes, int E_stride, int ES, const FwdParams &P) {
+    // bwd: the V region holds the dV accumulation table (V itself is read through L1), a dM table follows it, and
+    // there is no output staging.
+    int off_dM;
+    __host__ __device__ SmemLayout(int FP, int E_lanes, int E_stride, int ES, const FwdParams &P, bool bwd = false) {
         mstr = E_lanes | 1;
         vstr = FP | 1;
         off_bar = 0;                                   // 3 * kMaxSlots + 1 mbarriers, then the unit counter
@@ -92,14 +104,15 @@ struct SmemLayout {
         m_bytes = up(P.R2 * mstr * 8, 16);
         v_bytes = up(P.R2 * vstr * 8, 16);
         off_V = off_M + m_bytes;
-        off_e = up(off_V + v_bytes, 128);
+        off_dM = off_V + v_bytes;
+        off_e = up(off_dM + (bwd ? m_bytes : 0), 128);
         slot_floats = P.SPG * P.F * E_stride;
         rows_pad = up(P.SPG * P.F, 4);
         off_vals = up(off_e + P.n_slots * slot_floats * 4, 16);
         off_ids = up(off_vals + P.TPE * rows_pad * 4, 16);
         off_out = up(off_ids + P.TPE * rows_pad * 4, 128);
         out_floats = up((32 / ES) * kNR * P.E, 4);
-        total = off_out + (P.tma_store ? P.NW * out_floats * 4 : 0);
+        total = off_out + ((P.tma_store && !bwd) ? P.NW * out_floats * 4 : 0);
     }
 };
 
@@ -174,6 +187,147 @@ __device__ __forceinline__ void fused_first_pass(const float2 (&X)[FP], float2 t
     }
 }
 
+// Backward of one row pair (SURVEY.md 8a formulas; entmax.py:71-80 for the gate Jacobian).  Recomputes the gates
+// from the saved (tau, S), then
+//   ds = dz * z ;  dw_f = ds . e_f ;  w_f = p_f V_f -> out_wA ;  dV += p_f dw_f ;  dp_f = dw_f V_f
+//   gppr_f = p_f^(2-alpha) [p_f > 0] ;  q = sum dp gppr / sum gppr ;  dg_f = (dp_f - q) gppr_f -> out_gA
+//   dM'[x] += dg_f e_f[x]
+// X comes in as (alpha-1) g of both rows and is overwritten.
+template <int FP, bool EXACT, int EC, int ES, int E_STRIDE>
+__device__ __forceinline__ void backward_pair(const FwdParams &P, float2 (&X)[FP], const float *eb, const float2 *vrow,
+                                              float2 *dV_row, float *dM_row0, float *dM_row1, long long grow,
+                                              long long b, int r0, bool has1, bool valid, int c) {
+    const EntmaxParams &ep = P.ep;
+    const int F = P.F, E = P.E, R = P.R;
+    // saved threshold and normaliser
+    float2 tau, S;
+    tau.x = __ldg(P.in_tau + 2 * grow);
+    S.x = __ldg(P.in_tau + 2 * grow + 1);
+    tau.y = has1 ? __ldg(P.in_tau + 2 * grow + 2) : tau.x;
+    S.y = has1 ? __ldg(P.in_tau + 2 * grow + 3) : S.x;
+    const float2 invS = make_float2(__frcp_rn(S.x), __frcp_rn(S.y));
+    const float2 nt = make_float2(-tau.x, -tau.y);
+    // ds = dz * z on this lane's chunk of the embedding axis, as (x, x+1) pairs
+    float2 ds[kNR][EC / 2];
+#pragma unroll
+    for (int x = 0; x < EC; ++x) {
+        const int xx = c * EC + x;
+        float d0 = 0.f, d1 = 0.f;
+        if (xx < E) {
+            d0 = __ldg(P.in_dz + grow * E + xx) * __ldg(P.in_z + grow * E + xx);
+            if (has1) d1 = __ldg(P.in_dz + (grow + 1) * E + xx) * __ldg(P.in_z + (grow + 1) * E + xx);
+        }
+        if (x & 1) {
+            ds[0][x / 2].y = d0;
+            ds[1][x / 2].y = d1;
+        } else {
+            ds[0][x / 2].x = d0;
+            ds[1][x / 2].x = d1;
+        }
+    }
+    // mode constants for gppr = p^(2-alpha)
+    const float tma = 1.f - ep.am1;                     // 2 - alpha
+    const float c2 = tma * ep.q;                        // p^(2-alpha) = ex2(c2 lg2(u) - (2-alpha) lg2(S))
+    const float2 c3 = make_float2(-tma * fast_lg2(S.x), -tma * fast_lg2(S.y));
+    const float2 rsq = make_float2(rsqrtf(S.x), rsqrtf(S.y));
+
+    float2 G[FP];  // gppr; X is reused for t = dp * gppr
+    float2 A = make_float2(0.f, 0.f), Bq = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int f = 0; f < FP; ++f) {
+        if (EXACT || f < F) {
+            float2 e[EC / 2];
+            load_e_chunk<EC>(eb + f * E_STRIDE, e);
+            float2 p, g;  // normalised gate and its Jacobian factor
+            if (ep.mode == POW_SOFTMAX) {
+                p = fmul2(gate_unnorm2<POW_SOFTMAX>(X[f], nt, ep), invS);
+                g = p;
+            } else if (ep.mode == POW_LINEAR) {
+                const float2 u = relu2(fadd2(X[f], nt));
+                p = fmul2(u, invS);
+                g = make_float2(u.x > 0.f ? 1.f : 0.f, u.y > 0.f ? 1.f : 0.f);
+            } else if (ep.mode == POW_SQUARE) {
+                const float2 u = relu2(fadd2(X[f], nt));
+                p = fmul2(fmul2(u, u), invS);
+                g = fmul2(u, rsq);
+            } else {
+                const float2 u = relu2(fadd2(X[f], nt));
+                const float2 l = make_float2(fast_lg2(u.x), fast_lg2(u.y));
+                const float2 t1 = fmul2(l, splat2(ep.q));
+                p = fmul2(make_float2(fast_ex2(t1.x), fast_ex2(t1.y)), invS);
+                const float2 t2 = ffma2(l, splat2(c2), c3);
+                g = make_float2(u.x > 0.f ? fast_ex2(t2.x) : 0.f, u.y > 0.f ? fast_ex2(t2.y) : 0.f);
+            }
+            // dw_f = ds . e_f for both rows
+            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int x = 0; x < EC / 2; ++x) {
+                a0 = ffma2(e[x], ds[0][x], a0);
+                a1 = ffma2(e[x], ds[1][x], a1);
+            }
+            float dw0 = a0.x + a0.y, dw1 = a1.x + a1.y;
+#pragma unroll
+            for (int m = 1; m < ES; m <<= 1) {
+                dw0 += __shfl_xor_sync(0xffffffffu, dw0, m);
+                dw1 += __shfl_xor_sync(0xffffffffu, dw1, m);
+            }
+            const float2 dw = make_float2(dw0, dw1);
+            const float2 v = __ldg(vrow + f);
+            if (valid && c == 0) {
+                const float2 w = fmul2(p, v);  // armnet.py:36
+                float *wdst = P.out_wA + (b * F + f) * (long long)R + r0;
+                wdst[0] = w.x;
+                if (has1) wdst[1] = w.y;
+                const float2 pv = fmul2(p, dw);  // d values (summed over the batch)
+                atomicAdd(&dV_row[f].x, pv.x);
+                if (has1) atomicAdd(&dV_row[f].y, pv.y);
+            }
+            const float2 t = fmul2(fmul2(dw, v), g);  // dp * gppr
+            A = fadd2(A, t);
+            Bq = fadd2(Bq, g);
+            X[f] = t;
+            G[f] = g;
+        } else {
+            G[f] = make_float2(0.f, 0.f);
+        }
+    }
+    const float2 nq = make_float2(-__fdividef(A.x, Bq.x), -__fdividef(A.y, Bq.y));  // entmax.py:77
+    phase_fence();
+    float2 dM[kNR][EC / 2];
+#pragma unroll
+    for (int x = 0; x < EC / 2; ++x) dM[0][x] = dM[1][x] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int f = 0; f < FP; ++f) {
+        if (EXACT || f < F) {
+            const float2 dg = ffma2(nq, G[f], X[f]);  // dY*gppr - q*gppr (entmax.py:76,79)
+            if (valid && c == 0) {
+                float *gdst = P.out_gA + (b * F + f) * (long long)R + r0;
+                gdst[0] = dg.x;
+                if (has1) gdst[1] = dg.y;
+            }
+            float2 e[EC / 2];
+            load_e_chunk<EC>(eb + f * E_STRIDE, e);
+            const float2 g0 = splat2(dg.x), g1 = splat2(dg.y);
+#pragma unroll
+            for (int x = 0; x < EC / 2; ++x) {
+                dM[0][x] = ffma2(g0, e[x], dM[0][x]);
+                dM[1][x] = ffma2(g1, e[x], dM[1][x]);
+            }
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int x = 0; x < EC / 2; ++x) {
+            atomicAdd(dM_row0 + 2 * x, dM[0][x].x);
+            atomicAdd(dM_row0 + 2 * x + 1, dM[0][x].y);
+            if (has1) {
+                atomicAdd(dM_row1 + 2 * x, dM[1][x].x);
+                atomicAdd(dM_row1 + 2 * x + 1, dM[1][x].y);
+            }
+        }
+    }
+}
+
 // Gather of one tile into its slot, by one whole warp; ids / clamped values come from the epoch's preloaded arrays.
 template <int E_STRIDE>
 __device__ __forceinline__ void issue_tile_gather(const FwdParams &P, const SmemLayout &L, int lane, long long tile,
@@ -209,8 +363,9 @@ __device__ __forceinline__ void issue_tile_gather(const FwdParams &P, const Smem
     }
 }
 
-template <int FP, bool EXACT, int EC, int ES>
-__global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid_constant__ FwdParams P) {
+template <int FP, bool EXACT, int EC, int ES, bool BWD>
+__global__ void __launch_bounds__(BWD ? kBwdWarps * 32 : kMaxThreads, 1)
+    armnet_fwd_kernel(const __grid_constant__ FwdParams P) {
     static_assert(EC % 2 == 0, "EC must be even (float2/float4 shared-memory reads)");
     static_assert(ES == 1 || EC % 4 == 0, "split rows need 16-byte aligned chunks");
     static_assert(ES == 1 || ES == 2 || ES == 4 || ES == 8, "ES must be a power of two <= 8");
@@ -218,7 +373,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
     constexpr int E_STRIDE = round_up_c(E_LANES, 4);
     constexpr int PPW = 32 / ES;  // row pairs per warp-unit
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout L(FP, E_LANES, E_STRIDE, ES, P);
+    const SmemLayout L(FP, E_LANES, E_STRIDE, ES, P, BWD);
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     uint64_t *bar_empty = bar_full + kMaxSlots;
     uint64_t *bar_raw = bar_empty + kMaxSlots;
@@ -247,9 +402,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
         mbar_init(bar_par, 1);
         mbar_fence_init();
         // the pre-contracted parameter tables arrive by TMA while the ids are being preloaded
-        mbar_arrive_expect_tx(bar_par, (uint32_t)(L.m_bytes + L.v_bytes));
+        mbar_arrive_expect_tx(bar_par, (uint32_t)(L.m_bytes + (BWD ? 0 : L.v_bytes)));
         tma_load_bulk(Ms2, P.Mg2, (uint32_t)L.m_bytes, bar_par);
-        tma_load_bulk(Vs2, P.Vg2, (uint32_t)L.v_bytes, bar_par);
+        if (!BWD) tma_load_bulk(Vs2, P.Vg2, (uint32_t)L.v_bytes, bar_par);
+    }
+    float *dMs = reinterpret_cast<float *>(smem + L.off_dM);  // BWD: [R2][2][E_LANES] (+pad), same layout as Ms2
+    if (BWD) {  // Vs2 is the dV accumulation table in the backward kernel
+        for (int i = tid; i < (L.v_bytes + L.m_bytes) / 4; i += blockDim.x) reinterpret_cast<float *>(Vs2)[i] = 0.f;
     }
     for (int i = tid; i < NS * L.slot_floats; i += blockDim.x) es[i] = 0.f;  // pad lanes stay zero for good
     fence_proxy_async_smem();
@@ -417,6 +576,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
         }
         phase_fence();
 
+        if constexpr (BWD) {
+            backward_pair<FP, EXACT, EC, ES, E_STRIDE>(P, X, eb, P.Vg2 + j2 * L.vstr, Vs2 + j2 * L.vstr,
+                                                       dMs + j2 * (L.mstr * 2) + c * EC,
+                                                       dMs + j2 * (L.mstr * 2) + E_LANES + c * EC, grow, b0 + bl, r0,
+                                                       has1, valid, c);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[slot]);
+            continue;
+        }
+
         // ---- thresholds (entmax.py:44-61) and gates*values / log-space product (armnet.py:36,87), both rows together
         float2 tau;
         float2 acc[kNR][EC / 2];
@@ -557,19 +726,42 @@ __global__ void __launch_bounds__(kMaxThreads, 1) armnet_fwd_kernel(const __grid
         }
     }  // units of the epoch
     }  // epochs
-    if (P.tma_store && lane == 0) tma_store_wait_all<0>();
+    if constexpr (BWD) {
+        // flush this CTA's dV / dM' tables into the batch accumulators (one atomic per entry per CTA)
+        __syncthreads();
+        for (int i = tid; i < R2 * L.vstr; i += blockDim.x) {
+            const int j = i / L.vstr, f = i - j * L.vstr;
+            if (f < F) {
+                const float2 t = Vs2[i];
+                atomicAdd(P.acc_dV + (long long)(2 * j) * F + f, t.x);
+                if (2 * j + 1 < R) atomicAdd(P.acc_dV + (long long)(2 * j + 1) * F + f, t.y);
+            }
+        }
+        for (int i = tid; i < R2 * 2 * E_LANES; i += blockDim.x) {
+            const int j = i / (2 * E_LANES), rem = i - j * (2 * E_LANES);
+            const int n = rem / E_LANES, x = rem - n * E_LANES;
+            const int r = 2 * j + n;
+            if (x < E && r < R) atomicAdd(P.acc_dM + (long long)r * E + x, dMs[j * (L.mstr * 2) + n * E_LANES + x]);
+        }
+    } else {
+        if (P.tma_store && lane == 0) tma_store_wait_all<0>();
+    }
 }
 
-// One compiled shape of the kernel.
+// One compiled shape of the kernel (forward, and optionally backward).
 struct FwdInstance {
     int FP;
     int exact;  // FP == F required
     int EC;
     int ES;
     const void *kernel;
+    const void *kernel_bwd;  // null: no fused backward for this shape
 };
 
 #define ARMNET_FWD_INSTANCE(FP, EXACT, EC, ES) \
-    { FP, EXACT, EC, ES, (const void *)&armnet_fwd_kernel<FP, (EXACT) != 0, EC, ES> }
+    { FP, EXACT, EC, ES, (const void *)&armnet_fwd_kernel<FP, (EXACT) != 0, EC, ES, false>, nullptr }
+#define ARMNET_FWD_BWD_INSTANCE(FP, EXACT, EC, ES)                                            \
+    { FP, EXACT, EC, ES, (const void *)&armnet_fwd_kernel<FP, (EXACT) != 0, EC, ES, false>, \
+      (const void *)&armnet_fwd_kernel<FP, (EXACT) != 0, EC, ES, true> }
 
 }  // namespace armnet

@@ -10,7 +10,7 @@ import torch
 from . import _capi
 from ._capi import SOLVER_AUTO, SOLVER_BISECT, check, lib
 
-__all__ = ['embed_gather', 'entmax', 'fused_forward', 'new_error_flag', 'raise_if_bad_ids',
+__all__ = ['embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
            'SOLVER_AUTO', 'SOLVER_BISECT', 'last_launch_count']
 
 
@@ -189,3 +189,87 @@ def fused_forward(ids, values, table, bilinear_w, query, att_values, alpha, one_
         ptr('s'), ws.data_ptr(), err_flag.data_ptr() if err_flag is not None else None, _stream())
     check(rc, 'armnet_fused_fwd_f32')
     return z, extra
+
+
+def fused_bwd_supported(F, E):
+    return bool(lib.armnet_fused_bwd_supported(int(F), int(E)))
+
+
+def fused_backward(ids, values, table, bilinear_w, query, att_values, alpha, z, dz, tau, one_head=False,
+                   ld: Optional[int] = None, nemb: Optional[int] = None):
+    """armnet_fused_bwd_f32: returns (w [B,F,R], dg [B,F,R], dvalues [R,F], dm [R,E]); see include/armnet_b200.h."""
+    _need_cuda(ids, values, table, bilinear_w, query, att_values, z, dz, tau)
+    ids_c = ids.contiguous()
+    values, _ = _values_inplace(values)
+    table = _f32c(table, 'table')
+    W, Q, Vv = _f32c(bilinear_w, 'bilinear_w'), _f32c(query, 'query'), _f32c(att_values, 'values')
+    z, dz, tau = _f32c(z, 'z'), _f32c(dz, 'dz'), _f32c(tau, 'tau')
+    B, F = ids_c.shape
+    V = table.shape[0]
+    ld = table.shape[1] if ld is None else ld
+    E = table.shape[1] if nemb is None else nemb
+    if one_head:
+        D, K, O = W.shape[0], 1, Q.shape[0]
+    else:
+        K, O, D = Q.shape
+    R = K * O
+    dev = table.device
+    ws = torch.empty(max(lib.armnet_fused_workspace_bytes(F, E, K, O) // 4, 4), dtype=torch.float32, device=dev)
+    w = torch.empty(B, F, R, dtype=torch.float32, device=dev)
+    dg = torch.empty(B, F, R, dtype=torch.float32, device=dev)
+    dvals = torch.zeros(R, F, dtype=torch.float32, device=dev)
+    dm = torch.zeros(R, E, dtype=torch.float32, device=dev)
+    rc = lib.armnet_fused_bwd_f32(ids_c.data_ptr(), _ids_arg(ids_c), values.data_ptr(), table.data_ptr(), V, ld,
+                                  W.data_ptr(), Q.data_ptr(), Vv.data_ptr(), int(one_head), float(alpha), B, F, E, D,
+                                  K, O, z.data_ptr(), dz.data_ptr(), tau.data_ptr(), w.data_ptr(), dg.data_ptr(),
+                                  dvals.data_ptr(), dm.data_ptr(), ws.data_ptr(), None, _stream())
+    check(rc, 'armnet_fused_bwd_f32')
+    return w, dg, dvals, dm
+
+
+class _FusedInteractionFn(torch.autograd.Function):
+    """z = exp(sum_f entmax(g)_f V_f e_f) with the fused forward and backward kernels; gradients for the embedding
+    table (dense, like nn.Embedding(sparse=False)), bilinear_w, query and values. ids / values get none
+    (leaf inputs in train.py:104-109)."""
+
+    @staticmethod
+    def forward(ctx, table, bilinear_w, query, att_values, ids, values, alpha, one_head, solver):
+        z, extra = fused_forward(ids, values, table, bilinear_w, query, att_values, alpha, one_head=one_head,
+                                 solver=solver, want_tau=True)
+        ctx.save_for_backward(table, bilinear_w, query, att_values, ids, values, z, extra['tau'])
+        ctx.alpha, ctx.one_head = alpha, one_head
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        table, W, Q, Vv, ids, values, z, tau = ctx.saved_tensors
+        one_head = ctx.one_head
+        w, dg, dvals, dm = fused_backward(ids, values, table, W, Q, Vv, ctx.alpha, z, dz.contiguous(), tau,
+                                          one_head=one_head)
+        B, F = ids.shape
+        V, E = table.shape
+        D = W.shape[0] if one_head else W.shape[2]
+        scale = D ** -0.5
+        ds = dz * z                                                                 # [B,R,E]
+        if one_head:
+            Mt = torch.einsum('dx,od->ox', W, Q) * scale                            # [R,E]: scale * M[x][r]
+        else:
+            Mt = (torch.einsum('kxy,koy->kox', W, Q) * scale).reshape(-1, E)
+        de = torch.bmm(w, ds) + torch.matmul(dg, Mt)                                # [B,F,E]
+        dT = torch.zeros(V, E, dtype=table.dtype, device=table.device)
+        dT.index_add_(0, ids.reshape(-1).long(), (de * values.unsqueeze(2)).reshape(-1, E))
+        dms = dm * scale                                                            # [R,E]
+        if one_head:
+            dW = torch.einsum('ox,od->dx', dms, Q)
+            dQ = torch.einsum('ox,dx->od', dms, W)
+        else:
+            dmk = dms.reshape(Q.shape[0], Q.shape[1], E)
+            dW = torch.einsum('kox,koy->kxy', dmk, Q)
+            dQ = torch.einsum('kox,kxy->koy', dmk, W)
+        return dT, dW, dQ, dvals.reshape(Vv.shape), None, None, None, None, None
+
+
+def fused_interaction(table, bilinear_w, query, att_values, ids, values, alpha, one_head=False, solver=SOLVER_AUTO):
+    """Differentiable fused hot path (armnet.py:82-87): clamps `values` in place, returns z [B, K*O, E]."""
+    return _FusedInteractionFn.apply(table, bilinear_w, query, att_values, ids, values, float(alpha), bool(one_head),
+                                     int(solver))

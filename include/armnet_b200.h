@@ -107,6 +107,27 @@ int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values, const floa
                          const float *post_shift, float *out_z, float *out_tau, float *out_p, float *out_g,
                          float *out_s, void *workspace, int *err_flag, void *stream);
 
+/*
+ * Backward of the fused hot path w.r.t. its parameters (what autograd derives for models/armnet.py:82-87 with
+ * EntmaxBisectFunction.backward, utils/entmax.py:71-80).  Per (sample, neuron) row it rebuilds the gates from the
+ * (tau, sum) pairs the forward saved in out_tau and emits
+ *     out_w  [B,F,K*O]  w  = p * att_values                    (armnet.py:36)
+ *     out_dg [B,F,K*O]  dg = gradient w.r.t. the logits g      (entmax.py:76-79 applied to dp = (ds.e) * att_values)
+ * (row index fastest: coalesced, and the layout a batched GEMM over rows wants), and accumulates over the batch
+ *     acc_dvalues [K*O,F] += p * (ds . e)                      gradient of att_values
+ *     acc_dm      [K*O,E] += sum_f dg_f * e_f                  gradient of the pre-contracted matrix, unscaled
+ * with ds = dz * z.  The caller zeroes the accumulators, and finishes with dense products (host side, cuBLAS):
+ *     de[b,f,:] = sum_r out_w[b,f,r] ds[b,r,:] + d_k^-0.5 sum_r out_dg[b,f,r] M[:,r],   dT[id] += de * value,
+ *     dW, dQ from acc_dm.   z: forward output WITHOUT the arm_bn epilogue; values: already clamped by the forward.
+ * armnet_fused_bwd_supported() tells whether a backward kernel instance exists for (F, E).
+ */
+int armnet_fused_bwd_supported(int F, int E);
+int armnet_fused_bwd_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V, int64_t ld,
+                         const float *bilinear_w, const float *query, const float *att_values,
+                         int w_is_linear_layout, float alpha, int64_t B, int F, int E, int D, int K, int O,
+                         const float *z, const float *dz, const float *tau, float *out_w, float *out_dg,
+                         float *acc_dvalues, float *acc_dm, void *workspace, int *err_flag, void *stream);
+
 /* Number of kernels the last armnet_fused_fwd_f32 call on this thread launched (bench bookkeeping). */
 int armnet_last_launch_count(void);
 

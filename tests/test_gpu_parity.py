@@ -173,6 +173,28 @@ def test_train_step_matches_reference_autograd(golden):
         assert err <= 2e-4 * ref.abs().max().item() + 1e-5 * gmax, (n, err)
 
 
+def test_fused_backward_matches_unfused_autograd(golden):
+    """The fused backward kernel (+ cuBLAS finishing products) against the unfused autograd stages, same device."""
+    from armnet_b200 import ops
+    c = golden.cfg
+    if not ops.fused_bwd_supported(c['nfield'], c['nemb']):
+        pytest.skip('no backward instance for this shape')
+    d = dev()
+    gen = torch.Generator().manual_seed(4)
+    grads = []
+    for fused in (True, False):
+        m = build_model(golden, d).train()
+        m.fused_backward = fused
+        z = m._interaction_autograd({'id': golden.ids.to(d), 'value': golden.values.clone().to(d)})
+        if fused:
+            dz = torch.randn(z.shape, generator=gen).to(d)
+        (z * dz).sum().backward()
+        W = m.attn_layer.bilinear_w.weight if golden.one_head else m.attn_layer.bilinear_w
+        grads.append([m.embedding.embedding.weight.grad, W.grad, m.attn_layer.query.grad, m.attn_layer.values.grad])
+    for a, b, n in zip(grads[0], grads[1], ('table', 'bilinear_w', 'query', 'values')):
+        assert norm_rel(a.cpu(), b.cpu()) <= 5e-5, n
+
+
 # ---------------------------------------------------------------- edge cases and full-size properties
 
 def _criteo_state(seed=2025, nfeat=100000, nemb=10, nhid=128, nhead=4, nfield=39):
