@@ -1,0 +1,588 @@
+// The trailing dense MLP of ARMNetModel.forward in eval mode (models/layers.py:68-88 called from models/armnet.py:92,
+// models/armnet_1h.py:89): [Linear -> BatchNorm1d -> ReLU -> Dropout] x n -> Linear(., noutput).
+//
+// The first Linear ([B, K*O*E] x [K*O*E, mlp_nhid], 10.7 GFLOP at the Criteo shape) is the one true GEMM of the hot
+// path and runs on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+// fp32 parity (the reference multiplies in fp32, layers.py:73) is kept with the 3xTF32 split:
+//     x = x_hi + x_lo,  w = w_hi + w_lo   (hi = fp32 rounded to the 10-bit TF32 mantissa, lo = exact remainder)
+//     x.w ~= x_hi.w_hi + x_lo.w_hi + x_hi.w_lo          (dropped x_lo.w_lo ~ 2^-22 relative)
+// three kind::tf32 MMAs per K step into the same fp32 TMEM accumulator.  w_hi / w_lo are split once per weight
+// version (armnet_mlp_split_weight_f32); x is split in shared memory by the converter warps of the GEMM kernel.
+//
+// Everything after the first Linear (its bias + BatchNorm + ReLU, the narrow hidden layers, the output Linear) is
+// one CUDA-core kernel (mlp_tail_kernel): < 3 % of the FLOPs, latency bound, so one launch instead of ~8.
+#include <cuda.h>
+
+#include "entmax_pair.cuh"  // ffma2 / splat2 (packed fp32)
+
+namespace armnet {
+
+// ------------------------------------------------------------------ tile configuration of the tensor-core GEMM
+constexpr int GM = 128;      // rows of x per CTA (UMMA M, one TMEM lane per row)
+constexpr int GN = 256;      // output features per CTA (UMMA N, one TMEM column per feature)
+constexpr int GK = 32;       // floats of the reduction axis per stage = 128 bytes = one SWIZZLE_128B row
+constexpr int UK = 8;        // UMMA K for kind::tf32 (32 bytes)
+constexpr int G_STAGES = 2;
+constexpr int G_A_BYTES = GM * GK * 4;                              // 16 KB: x tile (hi after conversion)
+constexpr int G_B_BYTES = GN * GK * 4;                              // 32 KB: w_hi or w_lo tile
+constexpr int G_STAGE_BYTES = 2 * G_A_BYTES + 2 * G_B_BYTES;        // 96 KB: x_hi, x_lo, w_hi, w_lo
+constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int G_THREADS = 192;  // warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-5 converter + epilogue
+constexpr int G_CONV_THREADS = 128;
+
+// ------------------------------------------------------------------ PTX wrappers (tcgen05 / TMA tensor copies)
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_slot, uint32_t cols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {  // the same warp that allocated
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, both operands K-major, fp32 accumulate. Issued by ONE thread.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 lanes x 32 consecutive columns of fp32 accumulators -> 32 registers per thread (thread = TMEM lane = row)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major operand tile whose rows are 128 bytes, SWIZZLE_128B (what TMA wrote):
+// start address >> 4 in bits [0,14); leading byte offset (ignored for swizzled K-major, 1) in [16,30); stride byte
+// offset = 8 rows x 128 B = 1024 B >> 4 in [32,46); descriptor version 1 (sm_100) in [46,48); layout type 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem_tile) {
+    const uint64_t addr = (uint64_t)((smem_u32(smem_tile) & 0x3FFFFu) >> 4);
+    return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor, kind::tf32: D fp32 (bits 4-5 = 1), A/B TF32 (bits 7-9, 10-12 = 2), both K-major (bits 15,16 = 0),
+// N >> 3 in bits [17,23), M >> 4 in bits [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// fp32 -> nearest value with a 10-bit mantissa (ties away from zero in magnitude; the remainder x - hi is exact)
+__device__ __forceinline__ float tf32_hi(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+__global__ void split_tf32_kernel(const float *__restrict__ w, float *__restrict__ hi, float *__restrict__ lo,
+                                  long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float x = w[i];
+        const float h = tf32_hi(x);
+        hi[i] = h;
+        lo[i] = x - h;
+    }
+}
+
+struct GemmParams {
+    float *out;          // [splits][MB][N][32] partial sums over each split's slice of the reduction axis
+    int M, N, K;
+    int MB;              // ceil(M / 32) sample blocks
+    int kb_total;        // ceil(K / GK)
+    int splits;
+};
+
+// grid = (ceil(M/GM), ceil(N/GN), splits), 192 threads, one output tile per CTA.
+__global__ void __launch_bounds__(G_THREADS, 1)
+    mlp_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
+                           const __grid_constant__ CUtensorMap map_wl, const GemmParams P) {
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // stage s: x_hi | x_lo | w_hi | w_lo
+    auto s_xh = [&](int s) { return smem + s * G_STAGE_BYTES; };
+    auto s_xl = [&](int s) { return smem + s * G_STAGE_BYTES + G_A_BYTES; };
+    auto s_wh = [&](int s) { return smem + s * G_STAGE_BYTES + 2 * G_A_BYTES; };
+    auto s_wl = [&](int s) { return smem + s * G_STAGE_BYTES + 2 * G_A_BYTES + G_B_BYTES; };
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + G_STAGES * G_STAGE_BYTES);  // TMA landed (x, w_hi, w_lo)
+    uint64_t *bar_conv = bar_full + G_STAGES;                                            // x split into hi / lo
+    uint64_t *bar_empty = bar_conv + G_STAGES;                                           // MMAs of the stage retired
+    uint64_t *bar_acc = bar_empty + G_STAGES;                                            // accumulator complete
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_acc + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
+    const int kb0 = (int)((long long)P.kb_total * blockIdx.z / P.splits);
+    const int kb1 = (int)((long long)P.kb_total * (blockIdx.z + 1) / P.splits);
+    const int n_kb = kb1 - kb0;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_x);
+        prefetch_tensormap(&map_wh);
+        prefetch_tensormap(&map_wl);
+        for (int s = 0; s < G_STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_conv[s], G_CONV_THREADS / 32);
+            mbar_init(&bar_empty[s], 1);
+        }
+        mbar_init(bar_acc, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * GN);  // columns [0,GN): x_hi.w_hi, [GN,2GN): the two correction terms
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: x tile [GM x GK], w_hi / w_lo tiles [GN x GK]; out-of-range rows / columns arrive as zeros
+        if (lane == 0) {
+            for (int i = 0; i < n_kb; ++i) {
+                const int s = i % G_STAGES;
+                const uint32_t ph = (uint32_t)(i / G_STAGES) & 1u;
+                mbar_wait(&bar_empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&bar_full[s], (uint32_t)(G_A_BYTES + 2 * G_B_BYTES));
+                const int kc = (kb0 + i) * GK;
+                tma_load_2d(s_xh(s), &map_x, kc, m0, &bar_full[s]);
+                tma_load_2d(s_wh(s), &map_wh, kc, n0, &bar_full[s]);
+                tma_load_2d(s_wl(s), &map_wl, kc, n0, &bar_full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: per K step of 8, acc += x_hi.w_hi + x_lo.w_hi + x_hi.w_lo
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(GM, GN);
+            for (int i = 0; i < n_kb; ++i) {
+                const int s = i % G_STAGES;
+                const uint32_t ph = (uint32_t)(i / G_STAGES) & 1u;
+                mbar_wait(&bar_full[s], ph);
+                mbar_wait(&bar_conv[s], ph);
+                tc_fence_after();
+                const uint64_t d_xh = umma_desc_sw128(s_xh(s)), d_xl = umma_desc_sw128(s_xl(s));
+                const uint64_t d_wh = umma_desc_sw128(s_wh(s)), d_wl = umma_desc_sw128(s_wl(s));
+#pragma unroll
+                for (int k = 0; k < GK / UK; ++k) {
+                    const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);  // 32 bytes along K inside the swizzle atom
+                    // The tensor core rounds each accumulation towards zero; keeping the small correction terms in
+                    // their own accumulator shortens the rounding chain of the dominant term threefold.
+                    const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
+                    umma_tf32(tmem_acc, d_xh + adv, d_wh + adv, idesc, first);
+                    umma_tf32(tmem_acc + GN, d_xl + adv, d_wh + adv, idesc, first);
+                    umma_tf32(tmem_acc + GN, d_xh + adv, d_wl + adv, idesc, 1u);
+                }
+                umma_commit(&bar_empty[s]);  // frees the stage for the producer once these MMAs have read it
+            }
+            umma_commit(bar_acc);
+        }
+        __syncwarp();
+    } else {
+        // ===== converter warps: split the x tile TMA delivered into hi (in place) and lo, element-wise -- the
+        // swizzled placement is untouched, so the two tiles share the descriptor geometry
+        const int ct = threadIdx.x - 64;
+        for (int i = 0; i < n_kb; ++i) {
+            const int s = i % G_STAGES;
+            const uint32_t ph = (uint32_t)(i / G_STAGES) & 1u;
+            mbar_wait(&bar_full[s], ph);
+            float4 *xh = reinterpret_cast<float4 *>(s_xh(s));
+            float4 *xl = reinterpret_cast<float4 *>(s_xl(s));
+#pragma unroll
+            for (int j = 0; j < G_A_BYTES / 16 / G_CONV_THREADS; ++j) {
+                const int q = j * G_CONV_THREADS + ct;
+                const float4 v = xh[q];
+                float4 h, l;
+                h.x = tf32_hi(v.x);
+                h.y = tf32_hi(v.y);
+                h.z = tf32_hi(v.z);
+                h.w = tf32_hi(v.w);
+                l.x = v.x - h.x;
+                l.y = v.y - h.y;
+                l.z = v.z - h.z;
+                l.w = v.w - h.w;
+                xh[q] = h;
+                xl[q] = l;
+            }
+            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_conv[s]);
+        }
+        // ===== epilogue: TMEM -> registers -> global partial sums. Warp w may touch TMEM lanes [32 (w%4), +32).
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const int q4 = warp & 3;
+        const int row = m0 + q4 * 32 + lane;
+        // partial sums are stored in blocks of 32 samples, [split][m / 32][n][m % 32]: the 32 rows x 32 columns a warp
+        // holds are 4 KB of contiguous memory (coalesced, no power-of-two stride), and one CTA of the tail kernel
+        // (32 samples) reads one contiguous [N][32] block per split.
+        float *ocol = P.out + ((((long long)blockIdx.z * P.MB + (m0 >> 5) + q4) * P.N + n0) << 5) + lane;
+#pragma unroll 1
+        for (int c = 0; c < GN / 32; ++c) {
+            if (n0 + c * 32 >= P.N) break;  // warp-uniform
+            uint32_t r[32], r2[32];
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 32), r);
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(GN + c * 32), r2);
+            tmem_ld_wait();
+            if (row < P.M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n0 + c * 32 + j < P.N)
+                        ocol[(c * 32 + j) << 5] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_acc, 2 * GN);
+}
+
+// ------------------------------------------------------------------ everything after the first Linear
+// packed parameters (floats): a1[H] c1[H] | per further hidden layer: Wt[H_in=H][H] a[H] c[H] | Wf[NO][H] bf[NO]
+//   h1 = relu(sum_s partial[s] * a1 + c1)          a = bn.weight / sqrt(running_var + eps)  (layers.py:75, eval)
+//   h_{l+1} = relu((h_l . W_l^T) * a_l + c_l)       c = (linear.bias - running_mean) * a + bn.bias
+//   y = h_last . Wf^T + bf                                                                      (layers.py:81)
+constexpr int T_COLS = 256;      // output features per pass (one per thread column)
+constexpr int T_THREADS = 1024;  // T_COLS columns x 4 sample quarters
+constexpr int TS = 32;           // samples per CTA = one block of the partial-sum layout
+constexpr int TQ = TS / 4;       // samples per thread
+constexpr int TP = TS + 4;       // pitch (floats) of an activation row hT[feature][sample]: conflict-free float4 access
+constexpr int T_CH = 32;         // rows of W^T staged per chunk ([T_CH][T_COLS] floats = 32 KB), ring of n_buf chunks
+constexpr int T_MAXH = 512;
+constexpr int T_RED_WARPS = 8;
+
+struct TailParams {
+    const float *partials;  // [splits][MB][H][32]  (what the GEMM kernel writes)
+    const float *packed;
+    float *y;               // [B][NO]
+    long long B;
+    int splits, H, n_rest, NO;
+    int n_buf;              // W^T chunk buffers (2..4, as shared memory allows)
+};
+
+// One CTA = 32 samples through every layer after the first GEMM.  Activations live in shared memory feature-major
+// (hT[k][s]); thread (column n, quarter q) owns output feature n for 8 samples, reads the activations as
+// warp-broadcast float4 and feeds packed FFMA2; W^T chunks arrive by TMA bulk copies (one 1 KB row segment per lane of
+// warp 0) into a ring of buffers.  32 warps per SM hide the shared-memory latency.
+__global__ void __launch_bounds__(T_THREADS, 1) mlp_tail_kernel(const TailParams P) {
+    extern __shared__ __align__(128) unsigned char tsm_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tsm_raw);
+    float *wbuf = reinterpret_cast<float *>(tsm_raw + 128);
+    const int H = P.H;
+    const int NB = P.n_buf;
+    float *hA = wbuf + NB * T_CH * T_COLS;
+    float *hB = hA + H * TP;
+    float *red = hB + H * TP;  // [T_RED_WARPS][NO][TS]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int col = tid & (T_COLS - 1), q = tid / T_COLS;
+    const long long b0 = (long long)blockIdx.x * TS;
+    const int ns = (int)min((long long)TS, P.B - b0);
+    const long long MB = (P.B + TS - 1) / TS;
+    const float *pk = P.packed;
+    if (tid == 0) {
+        for (int i = 0; i < NB; ++i) mbar_init(&bar[i], 1);
+        mbar_fence_init();
+    }
+    // ---- first layer's epilogue: reduce the split-K partial sums, bias + BatchNorm (folded), ReLU.
+    // float4 t of this CTA's [H][32] block = feature t / 8, samples 4 (t % 8) .. +3: coalesced reads, conflict-free writes.
+    for (int t = tid; t < H * (TS / 4); t += T_THREADS) {
+        const int n = t >> 3, s4 = (t & 7) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int sp = 0; sp < P.splits; ++sp) {
+            const float4 u = __ldg(reinterpret_cast<const float4 *>(P.partials + (((long long)sp * MB + blockIdx.x) * H << 5)) + t);
+            v.x += u.x;
+            v.y += u.y;
+            v.z += u.z;
+            v.w += u.w;
+        }
+        const float a1 = pk[n], c1 = pk[H + n];
+        v.x = (s4 + 0 < ns) ? fmaxf(fmaf(v.x, a1, c1), 0.f) : 0.f;
+        v.y = (s4 + 1 < ns) ? fmaxf(fmaf(v.y, a1, c1), 0.f) : 0.f;
+        v.z = (s4 + 2 < ns) ? fmaxf(fmaf(v.z, a1, c1), 0.f) : 0.f;
+        v.w = (s4 + 3 < ns) ? fmaxf(fmaf(v.w, a1, c1), 0.f) : 0.f;
+        *reinterpret_cast<float4 *>(hA + n * TP + s4) = v;
+    }
+    pk += 2 * H;
+    __syncthreads();
+    // ---- further hidden layers
+    uint32_t it = 0;  // chunks consumed so far: buffer it % NB, mbarrier parity (it / NB) & 1
+    const int n_chunks = (H + T_CH - 1) / T_CH;
+    for (int l = 0; l < P.n_rest; ++l) {
+        const float *Wt = pk;  // [H][H], input feature major
+        const float *a = pk + (long long)H * H, *c = a + H;
+        for (int g0 = 0; g0 < H; g0 += T_COLS) {
+            const int ncols = min(T_COLS, H - g0);
+            auto issue = [&](int cidx, int buf) {  // whole warp 0
+                const int rows = min(T_CH, H - cidx * T_CH);
+                if (lane == 0) mbar_arrive_expect_tx(&bar[buf], (uint32_t)(rows * ncols * 4));
+                __syncwarp();
+                if (lane < rows)
+                    tma_load_bulk(wbuf + (buf * T_CH + lane) * T_COLS, Wt + (long long)(cidx * T_CH + lane) * H + g0,
+                                  (uint32_t)(ncols * 4), &bar[buf]);
+            };
+            if (warp == 0) {
+                for (int i = 0; i < NB && i < n_chunks; ++i) issue(i, (int)((it + i) % NB));
+            }
+            float2 acc[TQ / 2];
+#pragma unroll
+            for (int j = 0; j < TQ / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+            for (int ci = 0; ci < n_chunks; ++ci, ++it) {
+                const int buf = (int)(it % NB);
+                mbar_wait(&bar[buf], (it / NB) & 1u);
+                const int rows = min(T_CH, H - ci * T_CH);
+                if (col < ncols) {
+                    const float *wb = wbuf + buf * T_CH * T_COLS + col;
+                    const float *hrow = hA + (ci * T_CH) * TP + q * TQ;
+#pragma unroll 8
+                    for (int kk = 0; kk < rows; ++kk) {
+                        const float2 w2 = splat2(wb[kk * T_COLS]);
+                        const float4 *hp = reinterpret_cast<const float4 *>(hrow + kk * TP);
+#pragma unroll
+                        for (int j = 0; j < TQ / 4; ++j) {
+                            const float4 h = hp[j];  // warp-broadcast
+                            acc[2 * j] = ffma2(make_float2(h.x, h.y), w2, acc[2 * j]);
+                            acc[2 * j + 1] = ffma2(make_float2(h.z, h.w), w2, acc[2 * j + 1]);
+                        }
+                    }
+                }
+                __syncthreads();  // everyone is done with this buffer
+                if (warp == 0 && ci + NB < n_chunks) issue(ci + NB, buf);
+            }
+            if (col < ncols) {
+                const int n = g0 + col;
+                const float an = a[n], cn = c[n];
+#pragma unroll
+                for (int j = 0; j < TQ / 4; ++j) {
+                    float4 o;
+                    o.x = fmaxf(fmaf(acc[2 * j].x, an, cn), 0.f);
+                    o.y = fmaxf(fmaf(acc[2 * j].y, an, cn), 0.f);
+                    o.z = fmaxf(fmaf(acc[2 * j + 1].x, an, cn), 0.f);
+                    o.w = fmaxf(fmaf(acc[2 * j + 1].y, an, cn), 0.f);
+                    *reinterpret_cast<float4 *>(hB + n * TP + q * TQ + 4 * j) = o;
+                }
+            }
+        }
+        pk += (long long)H * H + 2 * H;
+        __syncthreads();
+        float *t = hA;
+        hA = hB;
+        hB = t;
+    }
+    // ---- output Linear (layers.py:81): lane = sample, 8 warps split the feature axis, then a shared-memory sum
+    const float *Wf = pk, *bf = pk + (long long)P.NO * H;
+    if (warp < T_RED_WARPS) {
+        const int kw0 = (int)((long long)H * warp / T_RED_WARPS), kw1 = (int)((long long)H * (warp + 1) / T_RED_WARPS);
+        for (int o = 0; o < P.NO; ++o) {
+            float accs = 0.f;
+            for (int k = kw0; k < kw1; ++k) accs = fmaf(hA[k * TP + lane], __ldg(Wf + (long long)o * H + k), accs);
+            red[(warp * P.NO + o) * TS + lane] = accs;
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < ns * P.NO; t += T_THREADS) {
+        const int sidx = t / P.NO, o = t - sidx * P.NO;
+        float v = bf[o];
+#pragma unroll
+        for (int w = 0; w < T_RED_WARPS; ++w) v += red[(w * P.NO + o) * TS + sidx];
+        P.y[(b0 + sidx) * P.NO + o] = v;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    // The driver entry point is resolved through the runtime, so the library has no link-time libcuda dependency.
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major [rows][cols] (pitch = cols), box [box_rows][GK], 128-byte swizzle, zeros outside the tensor.
+static int make_map(CUtensorMap *map, const float *base, long long rows, long long cols, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return ARMNET_ERR_CUDA;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)GK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld)", (int)r, rows, cols);
+        return ARMNET_ERR_CUDA;
+    }
+    return ARMNET_OK;
+}
+
+}  // namespace armnet
+
+using namespace armnet;
+
+extern "C" {
+
+int armnet_mlp_split_weight_f32(const float *w, int64_t n, float *w_hi, float *w_lo, void *stream) {
+    if (!w || !w_hi || !w_lo) {
+        set_error("armnet_mlp_split_weight_f32: null pointer");
+        return ARMNET_ERR_NULL;
+    }
+    if (n <= 0) return ARMNET_OK;
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, w_hi, w_lo, (long long)n);
+    ARMNET_CUDA_TRY(cudaGetLastError());
+    note_launches(1);
+    return ARMNET_OK;
+}
+
+int armnet_mlp_linear_splits(int64_t B, int K, int N) {
+    if (B <= 0 || K <= 0 || N <= 0) return 0;
+    DeviceInfo di;
+    if (get_device_info(&di) != ARMNET_OK) return 0;
+    const long long tiles = ((B + GM - 1) / GM) * ((N + GN - 1) / GN);
+    const int kb_total = (K + GK - 1) / GK;
+    // One wave of CTAs.  The tensor core rounds every accumulation towards zero, so the error grows with the length of
+    // the accumulation chain (K = 5120: 1.3e-5 unsplit, 3e-6 at 4 splits -- cuBLAS fp32 SGEMM: 3e-6); never run unsplit
+    // chains longer than 64 K-blocks.
+    long long s = di.sm_count / (tiles > 0 ? tiles : 1);
+    if (s < (kb_total + 63) / 64) s = (kb_total + 63) / 64;
+    if (s < 1) s = 1;
+    if (s > 16) s = 16;
+    if (s > kb_total) s = kb_total;
+    return (int)s;
+}
+
+int armnet_mlp_linear_tf32x3(const float *x, int64_t B, int K, const float *w_hi, const float *w_lo, int N, int splits,
+                             float *partials, void *stream) {
+    if (!x || !w_hi || !w_lo || !partials) {
+        set_error("armnet_mlp_linear_tf32x3: null pointer");
+        return ARMNET_ERR_NULL;
+    }
+    if (B <= 0 || K <= 0 || N <= 0 || splits <= 0 || splits > (K + GK - 1) / GK) {
+        set_error("armnet_mlp_linear_tf32x3: bad sizes B=%lld K=%d N=%d splits=%d", (long long)B, K, N, splits);
+        return ARMNET_ERR_SHAPE;
+    }
+    if (K % 4 != 0 || ((uintptr_t)x & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15) ||
+        ((uintptr_t)partials & 15)) {
+        set_error("armnet_mlp_linear_tf32x3: TMA needs 16-byte aligned rows (K %% 4 == 0) and base pointers");
+        return ARMNET_ERR_ALIGN;
+    }
+    CUtensorMap mx, mh, ml;
+    int rc;
+    if ((rc = make_map(&mx, x, B, K, GM)) != ARMNET_OK) return rc;
+    if ((rc = make_map(&mh, w_hi, N, K, GN)) != ARMNET_OK) return rc;
+    if ((rc = make_map(&ml, w_lo, N, K, GN)) != ARMNET_OK) return rc;
+    GemmParams P;
+    P.out = partials;
+    P.M = (int)B;
+    P.MB = (int)((B + 31) / 32);
+    P.N = N;
+    P.K = K;
+    P.kb_total = (K + GK - 1) / GK;
+    P.splits = splits;
+    static bool attr_set[64];
+    int dev = 0;
+    ARMNET_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        ARMNET_CUDA_TRY(cudaFuncSetAttribute(mlp_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             G_SMEM_BYTES));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    dim3 grid((unsigned)((B + GM - 1) / GM), (unsigned)((N + GN - 1) / GN), (unsigned)splits);
+    mlp_gemm_tf32x3_kernel<<<grid, G_THREADS, G_SMEM_BYTES, (cudaStream_t)stream>>>(mx, mh, ml, P);
+    ARMNET_CUDA_TRY(cudaGetLastError());
+    note_launches(1);
+    return ARMNET_OK;
+}
+
+size_t armnet_mlp_tail_packed_floats(int H, int n_rest, int NO) {
+    if (H <= 0 || n_rest < 0 || NO <= 0) return 0;
+    return (size_t)2 * H + (size_t)n_rest * ((size_t)H * H + 2 * (size_t)H) + (size_t)NO * H + NO;
+}
+
+int armnet_mlp_tail_f32(const float *partials, int splits, int64_t B, int H, int n_rest, int NO, const float *packed,
+                        float *y, void *stream) {
+    if (!partials || !packed || !y) {
+        set_error("armnet_mlp_tail_f32: null pointer");
+        return ARMNET_ERR_NULL;
+    }
+    if (B <= 0 || H <= 0 || n_rest < 0 || NO <= 0 || splits <= 0) {
+        set_error("armnet_mlp_tail_f32: bad sizes B=%lld H=%d n_rest=%d NO=%d splits=%d", (long long)B, H, n_rest, NO,
+                  splits);
+        return ARMNET_ERR_SHAPE;
+    }
+    if (H % 4 != 0 || H > T_MAXH || NO > 64 || ((uintptr_t)packed & 15) || ((uintptr_t)partials & 15)) {
+        set_error("armnet_mlp_tail_f32: hidden width %d / outputs %d not supported (H %% 4 == 0, H <= %d, NO <= 64)", H,
+                  NO, T_MAXH);
+        return ARMNET_ERR_UNSUPPORTED;
+    }
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc != ARMNET_OK) return rc;
+    int n_buf = 4;
+    size_t smem = 0;
+    for (; n_buf >= 2; --n_buf) {
+        smem = 128 + ((size_t)n_buf * T_CH * T_COLS + (size_t)2 * H * TP + (size_t)T_RED_WARPS * NO * TS) * sizeof(float);
+        if (smem <= (size_t)di.smem_optin) break;
+    }
+    if (n_buf < 2) {
+        set_error("armnet_mlp_tail_f32: hidden width %d needs %zu bytes of shared memory (> %d)", H, smem, di.smem_optin);
+        return ARMNET_ERR_UNSUPPORTED;
+    }
+    ARMNET_CUDA_TRY(cudaFuncSetAttribute(mlp_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TailParams P;
+    P.partials = partials;
+    P.packed = packed;
+    P.y = y;
+    P.B = B;
+    P.splits = splits;
+    P.H = H;
+    P.n_rest = n_rest;
+    P.NO = NO;
+    P.n_buf = n_buf;
+    mlp_tail_kernel<<<(unsigned)((B + TS - 1) / TS), T_THREADS, smem, (cudaStream_t)stream>>>(P);
+    ARMNET_CUDA_TRY(cudaGetLastError());
+    note_launches(1);
+    return ARMNET_OK;
+}
+
+}  // extern "C"

@@ -42,11 +42,17 @@ class Embedding(nn.Module):
 
 
 class MLP(nn.Module):
-    """layers.MLP (layers.py:68-88): [Linear -> BatchNorm1d -> ReLU -> Dropout] x nlayers -> Linear(., noutput).
-    Dense GEMMs: stock torch (cuBLAS) modules, identical state_dict keys ('mlp.<i>.weight', ...)."""
+    """layers.MLP (layers.py:68-88): [Linear -> BatchNorm1d -> ReLU -> Dropout] x nlayers -> Linear(., noutput),
+    identical state_dict keys ('mlp.<i>.weight', ...).
+
+    Eval mode without autograd on CUDA: the first Linear -- the one true GEMM of the path -- runs on the tcgen05
+    tensor cores (3xTF32 split, fp32 parity) and every layer after it in one CUDA-core kernel
+    (armnet_mlp_linear_tf32x3 / armnet_mlp_tail_f32). Training, or shapes TMA cannot address (ninput % 4 != 0),
+    use the stock torch modules (cuBLAS fp32)."""
 
     def __init__(self, ninput, nlayers, nhid, dropout, noutput=1):
         super().__init__()
+        self.ninput, self.nlayers, self.noutput = ninput, nlayers, noutput
         mods = []
         for _ in range(nlayers):
             mods += [nn.Linear(ninput, nhid), nn.BatchNorm1d(nhid), nn.ReLU(), nn.Dropout(p=dropout)]
@@ -55,6 +61,31 @@ class MLP(nn.Module):
             nhid = ninput
         mods.append(nn.Linear(nhid, noutput))
         self.mlp = nn.Sequential(*mods)
+        self.nhid = nhid
+        self.tensor_core = True     # host-side knob (not in state_dict)
+        self._cache_key = None
+        self._cache = None
+
+    def _fast_ok(self, x):
+        return (self.tensor_core and not self.training and not torch.is_grad_enabled() and x.is_cuda
+                and x.dtype == torch.float32 and x.dim() == 2 and self.nlayers >= 1 and self.ninput % 4 == 0
+                and self.nhid % 4 == 0 and self.nhid <= 512)
+
+    def _prepared(self):
+        """(w_hi, w_lo, packed tail parameters), rebuilt when any parameter / buffer changed."""
+        tensors = list(self.mlp.parameters()) + [b for b in self.mlp.buffers() if b.dtype.is_floating_point]
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if key != self._cache_key:
+            linears = [m for m in self.mlp if isinstance(m, nn.Linear)]
+            bns = [m for m in self.mlp if isinstance(m, nn.BatchNorm1d)]
+            w_hi, w_lo = ops.mlp_split_weight(linears[0].weight)
+            self._cache = (w_hi, w_lo, ops.mlp_pack_tail(linears, bns))
+            self._cache_key = key
+        return self._cache
 
     def forward(self, x):
+        if self._fast_ok(x):
+            w_hi, w_lo, packed = self._prepared()
+            partials = ops.mlp_first_linear(x, w_hi, w_lo)
+            return ops.mlp_tail(partials, packed, self.nlayers - 1, self.noutput, x.shape[0])
         return self.mlp(x)

@@ -10,7 +10,7 @@ import torch
 from . import _capi
 from ._capi import SOLVER_AUTO, SOLVER_BISECT, check, lib
 
-__all__ = ['embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
+__all__ = ['partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
            'SOLVER_AUTO', 'SOLVER_BISECT', 'last_launch_count']
 
 
@@ -273,3 +273,63 @@ def fused_interaction(table, bilinear_w, query, att_values, ids, values, alpha, 
     """Differentiable fused hot path (armnet.py:82-87): clamps `values` in place, returns z [B, K*O, E]."""
     return _FusedInteractionFn.apply(table, bilinear_w, query, att_values, ids, values, float(alpha), bool(one_head),
                                      int(solver))
+
+
+# ---------------------------------------------------------------------------------------------- trailing MLP (eval)
+def mlp_split_weight(w):
+    """nn.Linear weight [N,K] -> (w_hi, w_lo): TF32-rounded part and exact remainder (armnet_mlp_split_weight_f32)."""
+    _need_cuda(w)
+    w = _f32c(w.detach(), 'weight')
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    check(lib.armnet_mlp_split_weight_f32(w.data_ptr(), w.numel(), hi.data_ptr(), lo.data_ptr(), _stream()),
+          'armnet_mlp_split_weight_f32')
+    return hi, lo
+
+
+def mlp_first_linear(x, w_hi, w_lo, splits=None):
+    """x [B,K] . w^T on the tcgen05 tensor cores (3xTF32, fp32 accumulate) -> split-K partial sums in blocks of 32
+    samples, [splits, ceil(B/32), N, 32] (layers.py:73 without bias; partials_to_dense() gives F.linear(x, w))."""
+    _need_cuda(x, w_hi, w_lo)
+    x = _f32c(x, 'x')
+    B, K = x.shape
+    N = w_hi.shape[0]
+    assert w_hi.shape == (N, K) and w_lo.shape == (N, K) and w_hi.is_contiguous() and w_lo.is_contiguous()
+    if splits is None:
+        splits = lib.armnet_mlp_linear_splits(B, K, N)
+    out = torch.empty(splits, (B + 31) // 32, N, 32, dtype=torch.float32, device=x.device)
+    check(lib.armnet_mlp_linear_tf32x3(x.data_ptr(), B, K, w_hi.data_ptr(), w_lo.data_ptr(), N, splits,
+                                       out.data_ptr(), _stream()), 'armnet_mlp_linear_tf32x3')
+    return out
+
+
+def mlp_pack_tail(linears, bns):
+    """Pack the eval-mode parameters every layer after the first GEMM needs (include/armnet_b200.h,
+    armnet_mlp_tail_f32): linears = [L1, ..., Ln, Lout], bns = [BN1, ..., BNn]."""
+    with torch.no_grad():
+        parts = []
+        for i, (lin, bn) in enumerate(zip(linears[:-1], bns)):
+            a = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            c = (lin.bias - bn.running_mean) * a + bn.bias
+            if i > 0:
+                parts.append(lin.weight.t().contiguous().reshape(-1))
+            parts += [a, c]
+        parts += [linears[-1].weight.reshape(-1), linears[-1].bias]
+        return torch.cat([p.reshape(-1).float() for p in parts]).contiguous()
+
+
+def partials_to_dense(partials, B):
+    """[splits, MB, N, 32] partial sums -> the dense product [B, N] (test / validation helper)."""
+    S, MB, N, _ = partials.shape
+    return partials.sum(0).permute(0, 2, 1).reshape(MB * 32, N)[:B]
+
+
+def mlp_tail(partials, packed, n_rest, noutput, B):
+    """Everything after the first Linear's GEMM in one launch (armnet_mlp_tail_f32) -> y [B, noutput]."""
+    _need_cuda(partials, packed)
+    S, MB, H, _ = partials.shape
+    assert MB == (B + 31) // 32
+    assert packed.numel() == lib.armnet_mlp_tail_packed_floats(H, n_rest, noutput)
+    y = torch.empty(B, noutput, dtype=torch.float32, device=partials.device)
+    check(lib.armnet_mlp_tail_f32(partials.data_ptr(), S, B, H, n_rest, noutput, packed.data_ptr(), y.data_ptr(),
+                                  _stream()), 'armnet_mlp_tail_f32')
+    return y

@@ -128,6 +128,33 @@ int armnet_fused_bwd_f32(const void *ids, int ids_i32, float *values, const floa
                          const float *z, const float *dz, const float *tau, float *out_w, float *out_dg,
                          float *acc_dvalues, float *acc_dm, void *workspace, int *err_flag, void *stream);
 
+/*
+ * The trailing dense MLP in eval mode (models/layers.py:68-88, called at models/armnet.py:92, armnet_1h.py:89):
+ * [Linear -> BatchNorm1d -> ReLU -> Dropout] x n -> Linear(., noutput).  Dropout is the identity in eval mode.
+ *
+ * First Linear (layers.py:73, the only true GEMM of the path) on the tcgen05 tensor cores with the 3xTF32 split
+ * (x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, fp32 accumulation in TMEM), which reproduces fp32 SGEMM to ~1e-6 relative:
+ *   armnet_mlp_split_weight_f32   w [n] -> w_hi (TF32-rounded), w_lo = w - w_hi.  Once per weight version.
+ *   armnet_mlp_linear_splits      recommended split-K factor for (B, K, N) on the current device (>= 1).
+ *   armnet_mlp_linear_tf32x3      x [B,K] row-major, w_hi / w_lo [N,K] row-major (the nn.Linear weight layout)
+ *                                 -> partials [splits, ceil(B/32), N, 32] (blocks of 32 samples, sample fastest):
+ *                                 partial[s][b/32][n][b%32] = x[b, Ks] . w[n, Ks] over the s-th slice of the reduction axis; bias / BatchNorm / ReLU are applied by the tail kernel.
+ *                                 Needs K % 4 == 0 and 16-byte aligned base pointers (TMA), else ARMNET_ERR_ALIGN.
+ * Everything after it in ONE launch:
+ *   armnet_mlp_tail_f32           h1 = relu(sum_s partial[s] * a1 + c1); n_rest further hidden layers
+ *                                 h' = relu((h . W^T) * a + c); y = h . Wf^T + bf   (layers.py:73-81)
+ *     packed (floats): a1[H] c1[H] | n_rest x { Wt[H][H] (transposed weight: [in][out]), a[H], c[H] } | Wf[NO][H] bf[NO]
+ *     with a = bn.weight / sqrt(bn.running_var + eps), c = (linear.bias - bn.running_mean) * a + bn.bias.
+ *     armnet_mlp_tail_packed_floats(H, n_rest, NO) gives the length of `packed`.  y: [B, NO].
+ */
+int armnet_mlp_split_weight_f32(const float *w, int64_t n, float *w_hi, float *w_lo, void *stream);
+int armnet_mlp_linear_splits(int64_t B, int K, int N);
+int armnet_mlp_linear_tf32x3(const float *x, int64_t B, int K, const float *w_hi, const float *w_lo, int N, int splits,
+                             float *partials, void *stream);
+size_t armnet_mlp_tail_packed_floats(int H, int n_rest, int NO);
+int armnet_mlp_tail_f32(const float *partials, int splits, int64_t B, int H, int n_rest, int NO, const float *packed,
+                        float *y, void *stream);
+
 /* Number of kernels the last armnet_fused_fwd_f32 call on this thread launched (bench bookkeeping). */
 int armnet_last_launch_count(void);
 

@@ -1,0 +1,89 @@
+"""The trailing MLP in eval mode (layers.py:68-88): tcgen05 3xTF32 GEMM for the first Linear + one tail kernel,
+through the C ABI, against fp64 / stock torch fp32 evaluations of the same layers.
+Tolerance: max|a-b| / max|b| <= 1e-5 for the GEMM (cuBLAS fp32 SGEMM itself sits at ~4e-6 from fp64 at K=5120)."""
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+TOL_GEMM = 1e-5
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def nrel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max()).item()
+
+
+@pytest.mark.parametrize('B,K,N,splits', [(4096, 5120, 256, None), (4096, 5120, 256, 4), (512, 1280, 256, 1), (300, 132, 48, 3),
+                                           (130, 5120, 500, 2), (1, 64, 8, 1), (257, 36, 250, None)])
+def test_first_linear_3xtf32_matches_fp64(B, K, N, splits):
+    from armnet_b200 import ops
+    g = torch.Generator().manual_seed(B * 7 + K + N)
+    x = (torch.rand(B, K, generator=g) * 2 + 0.1).to(dev())          # like arm_bn(exp(.)): positive, O(1)
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).to(dev())
+    hi, lo = ops.mlp_split_weight(w)
+    assert torch.equal((hi.double() + lo.double()).float(), w)        # exact split
+    assert torch.all((hi.view(torch.int32) & 0x1FFF) == 0)           # hi is a TF32 value
+    part = ops.mlp_first_linear(x, hi, lo, splits=splits)
+    y = ops.partials_to_dense(part, B)
+    ref = x.double() @ w.double().t()
+    err = nrel(y, ref)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    err_sgemm = nrel(x @ w.t(), ref)
+    torch.backends.cuda.matmul.allow_tf32 = old
+    print(f'B={B} K={K} N={N} splits={part.shape[0]}: 3xTF32 err {err:.2e}, cuBLAS fp32 err {err_sgemm:.2e}')
+    assert err <= TOL_GEMM
+
+
+@pytest.mark.parametrize('ninput,nlayers,nhid,noutput,B', [(5120, 2, 256, 1, 4096), (640, 3, 200, 1, 513),
+                                                            (132, 1, 48, 2, 77), (2560, 2, 500, 1, 300)])
+def test_mlp_eval_fast_path_matches_stock_modules(ninput, nlayers, nhid, noutput, B):
+    from armnet_b200.layers import MLP
+    from armnet_b200 import ops
+    torch.manual_seed(ninput + nhid)
+    m = MLP(ninput, nlayers, nhid, 0.1, noutput=noutput)
+    with torch.no_grad():
+        for mod in m.mlp:
+            if isinstance(mod, nn.BatchNorm1d):                        # non-trivial running statistics / affine
+                mod.running_mean.normal_(0, 0.3)
+                mod.running_var.uniform_(0.5, 2.0)
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.normal_(0, 0.2)
+    m = m.to(dev()).eval()
+    x = torch.rand(B, ninput, device=dev()) * 2
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        y_fast = m(x)
+        n_launch = ops.last_launch_count()
+        m.tensor_core = False
+        y_ref = m(x)
+        y64 = m.double()(x.double())
+    torch.backends.cuda.matmul.allow_tf32 = old
+    assert n_launch == 1 and y_fast.shape == y_ref.shape == (B, noutput)
+    e_fast, e_ref = nrel(y_fast, y64), nrel(y_ref, y64)
+    print(f'fast path err vs fp64 {e_fast:.2e}; stock fp32 modules {e_ref:.2e}')
+    assert e_fast <= 1e-5
+    # the cache follows parameter updates
+    m = m.float()
+    m.tensor_core = True
+    with torch.no_grad():
+        m.mlp[0].weight.mul_(0.5)
+        y2 = m(x)
+        m.tensor_core = False
+        y2_ref = m(x)
+    assert nrel(y2, y2_ref) <= 1e-5
+
+
+def test_mlp_train_mode_uses_stock_path():
+    from armnet_b200.layers import MLP
+    m = MLP(64, 2, 32, 0.0).to(dev()).train()
+    x = torch.rand(16, 64, device=dev())
+    y = m(x)
+    y.sum().backward()
+    assert m.mlp[0].weight.grad is not None
