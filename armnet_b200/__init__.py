@@ -7,7 +7,8 @@ from .armnet_1h import SparseAttention
 from .entmax import EntmaxBisect, entmax_bisect
 from .layers import MLP, Embedding
 from .model_utils import create_model
+from .serving import BatchScorer
 
 __all__ = ['ARMNetModel', 'ARMNet1H', 'SparseAttLayer', 'SparseAttention', 'EntmaxBisect', 'entmax_bisect',
-           'Embedding', 'MLP', 'create_model', 'ops']
+           'Embedding', 'MLP', 'create_model', 'BatchScorer', 'ops']
 __version__ = '0.1.0'

@@ -269,10 +269,9 @@ __global__ void __launch_bounds__(G_THREADS, 1)
 //   h1 = relu(sum_s partial[s] * a1 + c1)          a = bn.weight / sqrt(running_var + eps)  (layers.py:75, eval)
 //   h_{l+1} = relu((h_l . W_l^T) * a_l + c_l)       c = (linear.bias - running_mean) * a + bn.bias
 //   y = h_last . Wf^T + bf                                                                      (layers.py:81)
-constexpr int T_COLS = 256;      // output features per pass (one per thread column)
-constexpr int T_THREADS = 1024;  // T_COLS columns x 4 sample quarters
+constexpr int T_COLS = 256;      // output features per pass
+constexpr int T_THREADS = 256;   // 8 warps: 2 halves of the reduction axis x 4 column blocks of 64
 constexpr int TS = 32;           // samples per CTA = one block of the partial-sum layout
-constexpr int TQ = TS / 4;       // samples per thread
 constexpr int TP = TS + 4;       // pitch (floats) of an activation row hT[feature][sample]: conflict-free float4 access
 constexpr int T_CH = 32;         // rows of W^T staged per chunk ([T_CH][T_COLS] floats = 32 KB), ring of n_buf chunks
 constexpr int T_MAXH = 512;
@@ -284,24 +283,25 @@ struct TailParams {
     float *y;               // [B][NO]
     long long B;
     int splits, H, n_rest, NO;
-    int n_buf;              // W^T chunk buffers (2..4, as shared memory allows)
+    int n_buf_log2;         // log2 of the number of W^T chunk buffers (4 or 2, as shared memory allows)
 };
 
 // One CTA = 32 samples through every layer after the first GEMM.  Activations live in shared memory feature-major
-// (hT[k][s]); thread (column n, quarter q) owns output feature n for 8 samples, reads the activations as
-// warp-broadcast float4 and feeds packed FFMA2; W^T chunks arrive by TMA bulk copies (one 1 KB row segment per lane of
-// warp 0) into a ring of buffers.  32 warps per SM hide the shared-memory latency.
+// (hT[k][s]).  A hidden layer is a register-tiled SGEMM: a warp covers 32 samples x 64 output features with 8 x 8
+// accumulators per thread (packed FFMA2), so one k step costs 4 LDS.128 per 32 FFMA2 -- shared-memory return bandwidth
+// (512 B per LDS.128, broadcast or not) is the limiter of a CUDA-core GEMM; W^T chunks arrive by TMA bulk copies (one
+// 1 KB row segment per lane of warp 0) into a ring of buffers, and the two halves of each chunk's rows go to warps
+// 0-3 / 4-7, whose partial sums meet in shared memory at the end of the layer.
 __global__ void __launch_bounds__(T_THREADS, 1) mlp_tail_kernel(const TailParams P) {
     extern __shared__ __align__(128) unsigned char tsm_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(tsm_raw);
     float *wbuf = reinterpret_cast<float *>(tsm_raw + 128);
     const int H = P.H;
-    const int NB = P.n_buf;
+    const int NBL = P.n_buf_log2, NB = 1 << NBL;
     float *hA = wbuf + NB * T_CH * T_COLS;
     float *hB = hA + H * TP;
     float *red = hB + H * TP;  // [T_RED_WARPS][NO][TS]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int col = tid & (T_COLS - 1), q = tid / T_COLS;
     const long long b0 = (long long)blockIdx.x * TS;
     const int ns = (int)min((long long)TS, P.B - b0);
     const long long MB = (P.B + TS - 1) / TS;
@@ -312,28 +312,44 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_tail_kernel(const TailParams
     }
     // ---- first layer's epilogue: reduce the split-K partial sums, bias + BatchNorm (folded), ReLU.
     // float4 t of this CTA's [H][32] block = feature t / 8, samples 4 (t % 8) .. +3: coalesced reads, conflict-free writes.
-    for (int t = tid; t < H * (TS / 4); t += T_THREADS) {
-        const int n = t >> 3, s4 = (t & 7) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+    const int n_f4 = H * (TS / 4);
+    for (int t0 = tid; t0 < n_f4; t0 += 4 * T_THREADS) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int sp = 0; sp < P.splits; ++sp) {
-            const float4 u = __ldg(reinterpret_cast<const float4 *>(P.partials + (((long long)sp * MB + blockIdx.x) * H << 5)) + t);
-            v.x += u.x;
-            v.y += u.y;
-            v.z += u.z;
-            v.w += u.w;
+            const float4 *src = reinterpret_cast<const float4 *>(P.partials + (((long long)sp * MB + blockIdx.x) * H << 5));
+            float4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                w[u] = (t0 + u * T_THREADS < n_f4) ? __ldg(src + t0 + u * T_THREADS) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u].x += w[u].x;
+                v[u].y += w[u].y;
+                v[u].z += w[u].z;
+                v[u].w += w[u].w;
+            }
         }
-        const float a1 = pk[n], c1 = pk[H + n];
-        v.x = (s4 + 0 < ns) ? fmaxf(fmaf(v.x, a1, c1), 0.f) : 0.f;
-        v.y = (s4 + 1 < ns) ? fmaxf(fmaf(v.y, a1, c1), 0.f) : 0.f;
-        v.z = (s4 + 2 < ns) ? fmaxf(fmaf(v.z, a1, c1), 0.f) : 0.f;
-        v.w = (s4 + 3 < ns) ? fmaxf(fmaf(v.w, a1, c1), 0.f) : 0.f;
-        *reinterpret_cast<float4 *>(hA + n * TP + s4) = v;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * T_THREADS;
+            if (t < n_f4) {
+                const int n = t >> 3, s4 = (t & 7) * 4;
+                const float a1 = pk[n], c1 = pk[H + n];
+                float4 o;
+                o.x = (s4 + 0 < ns) ? fmaxf(fmaf(v[u].x, a1, c1), 0.f) : 0.f;
+                o.y = (s4 + 1 < ns) ? fmaxf(fmaf(v[u].y, a1, c1), 0.f) : 0.f;
+                o.z = (s4 + 2 < ns) ? fmaxf(fmaf(v[u].z, a1, c1), 0.f) : 0.f;
+                o.w = (s4 + 3 < ns) ? fmaxf(fmaf(v[u].w, a1, c1), 0.f) : 0.f;
+                *reinterpret_cast<float4 *>(hA + n * TP + s4) = o;
+            }
+        }
     }
     pk += 2 * H;
     __syncthreads();
     // ---- further hidden layers
-    uint32_t it = 0;  // chunks consumed so far: buffer it % NB, mbarrier parity (it / NB) & 1
+    uint32_t it = 0;  // chunks consumed so far: buffer it % NB, mbarrier parity (it / NB) & 1 (NB a power of two)
     const int n_chunks = (H + T_CH - 1) / T_CH;
     for (int l = 0; l < P.n_rest; ++l) {
         const float *Wt = pk;  // [H][H], input feature major
@@ -349,46 +365,71 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_tail_kernel(const TailParams
                                   (uint32_t)(ncols * 4), &bar[buf]);
             };
             if (warp == 0) {
-                for (int i = 0; i < NB && i < n_chunks; ++i) issue(i, (int)((it + i) % NB));
+                for (int i = 0; i < NB && i < n_chunks; ++i) issue(i, (int)((it + i) & (NB - 1)));
             }
-            float2 acc[TQ / 2];
+            // thread tile: samples {4 sg .. +3, 16 + 4 sg .. +3} x features {4 cg .. +3, 32 + 4 cg .. +3} of the warp's 64
+            const int kh = warp >> 2, wc = (warp & 3) * 64, sg = lane >> 3, cg = lane & 7;
+            float2 acc[4][8];  // [sample pair][feature]
 #pragma unroll
-            for (int j = 0; j < TQ / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
             for (int ci = 0; ci < n_chunks; ++ci, ++it) {
-                const int buf = (int)(it % NB);
-                mbar_wait(&bar[buf], (it / NB) & 1u);
+                const int buf = (int)(it & (NB - 1));
+                mbar_wait(&bar[buf], (it >> NBL) & 1u);
                 const int rows = min(T_CH, H - ci * T_CH);
-                if (col < ncols) {
-                    const float *wb = wbuf + buf * T_CH * T_COLS + col;
-                    const float *hrow = hA + (ci * T_CH) * TP + q * TQ;
-#pragma unroll 8
-                    for (int kk = 0; kk < rows; ++kk) {
-                        const float2 w2 = splat2(wb[kk * T_COLS]);
-                        const float4 *hp = reinterpret_cast<const float4 *>(hrow + kk * TP);
+                const int r0 = kh ? rows / 2 : 0, r1 = kh ? rows : rows / 2;
+                const float *wb = wbuf + buf * T_CH * T_COLS + wc + 4 * cg;
+                const float *hrow = hA + (ci * T_CH) * TP + 4 * sg;
+#pragma unroll 4
+                for (int kk = r0; kk < r1; ++kk) {
+                    const float4 w0 = *reinterpret_cast<const float4 *>(wb + kk * T_COLS);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(wb + kk * T_COLS + 32);
+                    const float4 h0 = *reinterpret_cast<const float4 *>(hrow + kk * TP);
+                    const float4 h1 = *reinterpret_cast<const float4 *>(hrow + kk * TP + 16);
+                    const float2 hp[4] = {make_float2(h0.x, h0.y), make_float2(h0.z, h0.w), make_float2(h1.x, h1.y),
+                                          make_float2(h1.z, h1.w)};
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                        for (int j = 0; j < TQ / 4; ++j) {
-                            const float4 h = hp[j];  // warp-broadcast
-                            acc[2 * j] = ffma2(make_float2(h.x, h.y), w2, acc[2 * j]);
-                            acc[2 * j + 1] = ffma2(make_float2(h.z, h.w), w2, acc[2 * j + 1]);
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 w2 = splat2(wv[j]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[i][j] = ffma2(hp[i], w2, acc[i][j]);
                     }
                 }
                 __syncthreads();  // everyone is done with this buffer
                 if (warp == 0 && ci + NB < n_chunks) issue(ci + NB, buf);
             }
-            if (col < ncols) {
-                const int n = g0 + col;
-                const float an = a[n], cn = c[n];
+            // the upper half of the reduction axis hands its sums to the lower half through the (now idle) chunk ring
+            float2 *xch = reinterpret_cast<float2 *>(wbuf);
+            if (kh == 1) {
 #pragma unroll
-                for (int j = 0; j < TQ / 4; ++j) {
-                    float4 o;
-                    o.x = fmaxf(fmaf(acc[2 * j].x, an, cn), 0.f);
-                    o.y = fmaxf(fmaf(acc[2 * j].y, an, cn), 0.f);
-                    o.z = fmaxf(fmaf(acc[2 * j + 1].x, an, cn), 0.f);
-                    o.w = fmaxf(fmaf(acc[2 * j + 1].y, an, cn), 0.f);
-                    *reinterpret_cast<float4 *>(hB + n * TP + q * TQ + 4 * j) = o;
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) xch[(i * 8 + j) * 128 + (tid - 128)] = acc[i][j];
+            }
+            __syncthreads();
+            if (kh == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int cl = wc + (j < 4 ? 4 * cg + j : 32 + 4 * cg + (j - 4));  // feature inside this pass
+                    if (cl < ncols) {
+                        const int n = g0 + cl;
+                        const float an = a[n], cn = c[n];
+                        float o[8];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 t = xch[(i * 8 + j) * 128 + tid];
+                            o[2 * i] = fmaxf(fmaf(acc[i][j].x + t.x, an, cn), 0.f);
+                            o[2 * i + 1] = fmaxf(fmaf(acc[i][j].y + t.y, an, cn), 0.f);
+                        }
+                        *reinterpret_cast<float4 *>(hB + n * TP + 4 * sg) = make_float4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<float4 *>(hB + n * TP + 16 + 4 * sg) = make_float4(o[4], o[5], o[6], o[7]);
+                    }
                 }
             }
+            fence_proxy_async_smem();  // generic accesses to the exchange area before the next TMA writes into it
+            __syncthreads();           // the exchange area is a chunk buffer again
         }
         pk += (long long)H * H + 2 * H;
         __syncthreads();
@@ -560,7 +601,7 @@ int armnet_mlp_tail_f32(const float *partials, int splits, int64_t B, int H, int
     if (rc != ARMNET_OK) return rc;
     int n_buf = 4;
     size_t smem = 0;
-    for (; n_buf >= 2; --n_buf) {
+    for (; n_buf >= 2; n_buf -= 2) {
         smem = 128 + ((size_t)n_buf * T_CH * T_COLS + (size_t)2 * H * TP + (size_t)T_RED_WARPS * NO * TS) * sizeof(float);
         if (smem <= (size_t)di.smem_optin) break;
     }
@@ -578,7 +619,7 @@ int armnet_mlp_tail_f32(const float *partials, int splits, int64_t B, int H, int
     P.H = H;
     P.n_rest = n_rest;
     P.NO = NO;
-    P.n_buf = n_buf;
+    P.n_buf_log2 = n_buf == 4 ? 2 : 1;
     mlp_tail_kernel<<<(unsigned)((B + TS - 1) / TS), T_THREADS, smem, (cudaStream_t)stream>>>(P);
     ARMNET_CUDA_TRY(cudaGetLastError());
     note_launches(1);

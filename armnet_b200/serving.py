@@ -1,0 +1,118 @@
+"""Pipelined scoring of HOST batches with a drop-in ARMNetModel (eval mode): what a serving process calls.
+
+The reference scores a batch with `y = model(batch)` after `.cuda(non_blocking=True)` copies and then syncs on
+`.item()` / `.cpu()` every batch (train.py:104-122).  BatchScorer keeps the same inputs and outputs
+(pinned host `id` [B,F] int64 / `value` [B,F] float32 in, host `y` [B] out) but overlaps the three phases of
+consecutive batches on the device:
+
+    copy stream     H2D(i+1)            H2D(i+2)
+    compute stream  forward(i) D2H(i)   forward(i+1) D2H(i+1)
+
+Each slot owns static device buffers, so the whole forward of a slot (attention pre-contraction, fused
+lookup+interaction kernel, tcgen05 GEMM, MLP tail kernel) is captured once in a CUDA graph and replayed: one graph
+launch per batch instead of ~6 kernel launches plus allocator traffic.  Nothing here computes: the arithmetic is the
+same kernels ARMNetModel.forward launches.
+
+Unlike ARMNetModel.forward, the caller's host `value` tensor is NOT clamped in place (the clamp of armnet.py:82 is
+applied to the device copy).
+"""
+import torch
+
+__all__ = ['BatchScorer']
+
+
+class _Slot:
+    def __init__(self, B, F, dev, ids_dtype):
+        self.ids = torch.zeros(B, F, dtype=ids_dtype, device=dev)
+        self.vals = torch.ones(B, F, dtype=torch.float32, device=dev)
+        self.y_host = None
+        self.y_dev = None
+        self.graph = None
+        self.ev_in = torch.cuda.Event()
+        self.ev_done = torch.cuda.Event()
+        self.used = False
+
+
+class BatchScorer:
+    def __init__(self, model, batch_size, nfield, depth=2, use_graph=True, ids_dtype=torch.int64):
+        p = next(model.parameters())
+        if not p.is_cuda:
+            raise RuntimeError('BatchScorer needs the model on a CUDA device (armnet_b200 has no CPU path)')
+        if model.training:
+            raise RuntimeError('BatchScorer scores in eval mode: call model.eval() first')
+        if getattr(model, 'validate_ids', False):
+            raise RuntimeError('validate_ids synchronises every batch; check ids upstream or use model(x) directly')
+        self.model, self.dev = model, p.device
+        self.B, self.F, self.depth, self.use_graph = batch_size, nfield, depth, use_graph
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.compute_stream = torch.cuda.Stream(self.dev)
+        self.slots = [_Slot(batch_size, nfield, self.dev, ids_dtype) for _ in range(depth)]
+        self.n_submitted = 0
+        self._prepare()
+
+    def _forward(self, slot):
+        with torch.no_grad():
+            return self.model({'id': slot.ids, 'value': slot.vals}).reshape(-1)
+
+    def _prepare(self):
+        """Warm every lazily built cache (padded table, folded BatchNorm, split weights), then capture one graph per slot."""
+        cs = self.compute_stream
+        cs.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(cs):
+            for s in self.slots:
+                for _ in range(2):
+                    y = self._forward(s)
+                s.y_host = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+        cs.synchronize()
+        if not self.use_graph:
+            return
+        for s in self.slots:
+            s.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(s.graph, stream=cs):
+                s.y_dev = self._forward(s)
+        cs.synchronize()
+
+    def submit(self, ids_host, values_host):
+        """Enqueue one batch (pinned host tensors [B,F]); returns a ticket for result(). At most `depth` tickets may be
+        outstanding: result(t) must have been called before submit() reuses its slot."""
+        if tuple(ids_host.shape) != (self.B, self.F) or tuple(values_host.shape) != (self.B, self.F):
+            raise ValueError(f'BatchScorer was built for batches of shape {(self.B, self.F)}')
+        t = self.n_submitted
+        s = self.slots[t % self.depth]
+        if s.used:
+            self.copy_stream.wait_event(s.ev_done)       # the slot's previous forward + D2H are done with its buffers
+        with torch.cuda.stream(self.copy_stream):
+            s.ids.copy_(ids_host, non_blocking=True)
+            s.vals.copy_(values_host, non_blocking=True)
+            s.ev_in.record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(s.ev_in)
+            if s.graph is not None:
+                s.graph.replay()
+                y = s.y_dev
+            else:
+                y = self._forward(s)
+            s.y_host.copy_(y, non_blocking=True)
+            s.ev_done.record(self.compute_stream)
+        s.used = True
+        self.n_submitted += 1
+        return t
+
+    def result(self, ticket):
+        """Host tensor y [B] of a submitted batch (blocks until its D2H copy has landed). The tensor is the slot's pinned
+        buffer: consume or clone it before `depth` further batches are submitted."""
+        if not (self.n_submitted - self.depth <= ticket < self.n_submitted):
+            raise ValueError('ticket is not outstanding')
+        s = self.slots[ticket % self.depth]
+        s.ev_done.synchronize()
+        return s.y_host
+
+    def score(self, batches):
+        """Convenience: iterate over (ids_host, values_host) pairs, yield cloned host results in order."""
+        pending = []
+        for ids_h, vals_h in batches:
+            if len(pending) == self.depth:
+                yield self.result(pending.pop(0)).clone()
+            pending.append(self.submit(ids_h, vals_h))
+        for t in pending:
+            yield self.result(t).clone()

@@ -87,3 +87,27 @@ def test_mlp_train_mode_uses_stock_path():
     y = m(x)
     y.sum().backward()
     assert m.mlp[0].weight.grad is not None
+
+
+@pytest.mark.parametrize('use_graph', [True, False])
+def test_batch_scorer_matches_module_forward(use_graph):
+    """serving.BatchScorer (pipelined copies, CUDA-graph replay) returns exactly what model(x) returns."""
+    import armnet_b200 as ab
+    torch.manual_seed(3)
+    F, V, B = 39, 5000, 256
+    model = ab.ARMNetModel(F, V, 10, 4, 1.7, 32, 2, 64, 0.0, False, 2, 32).to(dev()).eval()
+    g = torch.Generator().manual_seed(11)
+    batches = [(torch.randint(0, V, (B, F), generator=g).pin_memory(),
+                (torch.rand(B, F, generator=g) * 1.3).pin_memory()) for _ in range(5)]
+    want = []
+    with torch.no_grad():
+        for ids, vals in batches:
+            want.append(model({'id': ids.to(dev()), 'value': vals.clone().to(dev())}).cpu())
+    scorer = ab.BatchScorer(model, B, F, depth=2, use_graph=use_graph)
+    got = list(scorer.score(batches))
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert torch.equal(batches[0][1], batches[0][1].clone())     # host values are not clamped in place
+    with pytest.raises(ValueError):
+        scorer.submit(batches[0][0][:10], batches[0][1][:10])
