@@ -47,9 +47,9 @@ WORKLOADS = {
                mlp_nlayer=2, mlp_nhid=256),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of armnet_fwd_kernel from the committed `ncu --set full`
-# capture (profiles/r1_v3_fwd_summary.md): 21.9 MB read + 25.4 MB written. Below the algorithmic 92.2 MB because part
+# capture (profiles/r1_v5_summary.md, r1_v5_fwd_ncu.txt): 21.82 MB read + 25.13 MB written. Below the algorithmic 92.2 MB because part
 # of the 84 MB output is still dirty in the 126 MB L2 when the kernel ends; no re-reads.
-NCU_TRAFFIC_BYTES = {'c2a': 47289344}
+NCU_TRAFFIC_BYTES = {'c2a': 46956288}
 METRIC = 'CTR samples/sec (bsz=4096, Criteo-shape) at 1/2/4/8 B200; HBM GB/s vs roofline'
 
 
