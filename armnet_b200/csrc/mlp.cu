@@ -12,6 +12,7 @@
 // Everything after the first Linear (its bias + BatchNorm + ReLU, the narrow hidden layers, the output Linear) is
 // one CUDA-core kernel (mlp_tail_kernel): < 3 % of the FLOPs, latency bound, so one launch instead of ~8.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "entmax_pair.cuh"  // ffma2 / splat2 (packed fp32)
 
@@ -262,6 +263,214 @@ __global__ void __launch_bounds__(G_THREADS, 1)
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_acc, 2 * GN);
+}
+
+// ------------------------------------------------------------------ the same GEMM on a CTA PAIR (cta_group::2)
+// Two CTAs of a cluster (the two SMs of a TPC) share one 256 x 256 output tile: each holds 128 rows of x and HALF of
+// the W tile (128 of the 256 output features); tcgen05.mma.cta_group::2 (issued by the leader CTA only) multiplies
+// the pair's 256 rows with all 256 features, each SM's tensor core reading only its own shared memory.  Per SM and
+// K step that is 4 KB (x) + 4 KB (W half) of operand reads instead of 4 + 8, 48 KB instead of 80 KB of TMA traffic per
+// stage, and 64 KB stages -> a 3-deep ring.
+//   barriers, per stage:  bar_x    (own CTA)   own x tile landed             -> own converter warps
+//                         bar_w    (leader)    both CTAs' W halves landed    -> MMA issuer   (TMA ...cta_group::2 signals
+//                                                                               the leader's barrier from either CTA)
+//                         bar_conv (leader)    8 converter warps (2 CTAs) done, rank 1 arrives through the cluster
+//                         bar_empty(each CTA)  tcgen05.commit ...multicast::cluster from the leader frees the stage in both
+constexpr int G2_STAGES = 3;
+constexpr int G2_BH_BYTES = (GN / 2) * GK * 4;                        // 16 KB: this CTA's half of a W tile
+constexpr int G2_STAGE_BYTES = 2 * G_A_BYTES + 2 * G2_BH_BYTES;       // 64 KB
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA 0 of the cluster
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar))
+        : "memory");
+}
+// TMA tile load whose completion bytes are counted on the LEADER CTA's barrier (bit 24 of a shared::cluster address is
+// the CTA rank inside the pair)
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *smem_slot, uint32_t cols) {  // one full warp in EACH CTA
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {  // arrives on `bar` in BOTH CTAs
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+
+// grid = (2 * ceil(M/256), ceil(N/GN), splits), clusters of 2 along x, 192 threads per CTA.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
+    mlp_gemm_tf32x3_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
+                                const __grid_constant__ CUtensorMap map_wl, const GemmParams P) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    auto s_xh = [&](int s) { return smem + s * G2_STAGE_BYTES; };
+    auto s_xl = [&](int s) { return smem + s * G2_STAGE_BYTES + G_A_BYTES; };
+    auto s_wh = [&](int s) { return smem + s * G2_STAGE_BYTES + 2 * G_A_BYTES; };
+    auto s_wl = [&](int s) { return smem + s * G2_STAGE_BYTES + 2 * G_A_BYTES + G2_BH_BYTES; };
+    uint64_t *bar_x = reinterpret_cast<uint64_t *>(smem + G2_STAGES * G2_STAGE_BYTES);
+    uint64_t *bar_w = bar_x + G2_STAGES;
+    uint64_t *bar_conv = bar_w + G2_STAGES;
+    uint64_t *bar_empty = bar_conv + G2_STAGES;
+    uint64_t *bar_acc = bar_empty + G2_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_acc + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int m0 = blockIdx.x * GM;                       // blockIdx.x = 2 * pair + rank
+    const int n0 = blockIdx.y * GN, nh = n0 + (int)rank * (GN / 2);
+    const int kb0 = (int)((long long)P.kb_total * blockIdx.z / P.splits);
+    const int kb1 = (int)((long long)P.kb_total * (blockIdx.z + 1) / P.splits);
+    const int n_kb = kb1 - kb0;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_x);
+        prefetch_tensormap(&map_wh);
+        prefetch_tensormap(&map_wl);
+        for (int s = 0; s < G2_STAGES; ++s) {
+            mbar_init(&bar_x[s], 1);
+            mbar_init(&bar_w[s], 1);
+            mbar_init(&bar_conv[s], 2 * (G_CONV_THREADS / 32));
+            mbar_init(&bar_empty[s], 1);
+        }
+        mbar_init(bar_acc, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 2 * GN);
+    tc_fence_before();
+    cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals across the pair
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < n_kb; ++i) {
+                const int s = i % G2_STAGES;
+                const uint32_t ph = (uint32_t)(i / G2_STAGES) & 1u;
+                mbar_wait(&bar_empty[s], ph ^ 1u);
+                const int kc = (kb0 + i) * GK;
+                mbar_arrive_expect_tx(&bar_x[s], (uint32_t)G_A_BYTES);
+                tma_load_2d(s_xh(s), &map_x, kc, m0, &bar_x[s]);
+                if (leader) mbar_arrive_expect_tx(&bar_w[s], (uint32_t)(4 * G2_BH_BYTES));  // both halves, both CTAs
+                tma_load_2d_pair(s_wh(s), &map_wh, kc, nh, &bar_w[s]);
+                tma_load_2d_pair(s_wl(s), &map_wl, kc, nh, &bar_w[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(2 * GM, GN);
+            for (int i = 0; i < n_kb; ++i) {
+                const int s = i % G2_STAGES;
+                const uint32_t ph = (uint32_t)(i / G2_STAGES) & 1u;
+                mbar_wait(&bar_w[s], ph);
+                mbar_wait(&bar_conv[s], ph);
+                tc_fence_after();
+                const uint64_t d_xh = umma_desc_sw128(s_xh(s)), d_xl = umma_desc_sw128(s_xl(s));
+                const uint64_t d_wh = umma_desc_sw128(s_wh(s)), d_wl = umma_desc_sw128(s_wl(s));
+#pragma unroll
+                for (int k = 0; k < GK / UK; ++k) {
+                    const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);
+                    const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
+                    umma_tf32_pair(tmem_acc, d_xh + adv, d_wh + adv, idesc, first);
+                    umma_tf32_pair(tmem_acc + GN, d_xl + adv, d_wh + adv, idesc, first);
+                    umma_tf32_pair(tmem_acc + GN, d_xh + adv, d_wl + adv, idesc, 1u);
+                }
+                umma_commit_pair(&bar_empty[s]);
+            }
+            umma_commit_pair(bar_acc);
+        }
+        __syncwarp();
+    } else {
+        const int ct = threadIdx.x - 64;
+        for (int i = 0; i < n_kb; ++i) {
+            const int s = i % G2_STAGES;
+            const uint32_t ph = (uint32_t)(i / G2_STAGES) & 1u;
+            mbar_wait(&bar_x[s], ph);
+            float4 *xh = reinterpret_cast<float4 *>(s_xh(s));
+            float4 *xl = reinterpret_cast<float4 *>(s_xl(s));
+#pragma unroll
+            for (int j = 0; j < G_A_BYTES / 16 / G_CONV_THREADS; ++j) {
+                const int q = j * G_CONV_THREADS + ct;
+                const float4 v = xh[q];
+                float4 h, l;
+                h.x = tf32_hi(v.x);
+                h.y = tf32_hi(v.y);
+                h.z = tf32_hi(v.z);
+                h.w = tf32_hi(v.w);
+                l.x = v.x - h.x;
+                l.y = v.y - h.y;
+                l.z = v.z - h.z;
+                l.w = v.w - h.w;
+                xh[q] = h;
+                xl[q] = l;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&bar_conv[s]);
+        }
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const int q4 = warp & 3;
+        const int row = m0 + q4 * 32 + lane;
+        float *ocol = P.out + ((((long long)blockIdx.z * P.MB + (m0 >> 5) + q4) * P.N + n0) << 5) + lane;
+#pragma unroll 1
+        for (int c = 0; c < GN / 32; ++c) {
+            if (n0 + c * 32 >= P.N) break;  // warp-uniform
+            uint32_t r[32], r2[32];
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 32), r);
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(GN + c * 32), r2);
+            tmem_ld_wait();
+            if (row < P.M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n0 + c * 32 + j < P.N)
+                        ocol[(c * 32 + j) << 5] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer can still signal / multicast into this CTA
+    if (warp == 1) tmem_dealloc_pair(tmem_acc, 2 * GN);
 }
 
 // ------------------------------------------------------------------ everything after the first Linear
@@ -550,8 +759,9 @@ int armnet_mlp_linear_tf32x3(const float *x, int64_t B, int K, const float *w_hi
     CUtensorMap mx, mh, ml;
     int rc;
     if ((rc = make_map(&mx, x, B, K, GM)) != ARMNET_OK) return rc;
-    if ((rc = make_map(&mh, w_hi, N, K, GN)) != ARMNET_OK) return rc;
-    if ((rc = make_map(&ml, w_lo, N, K, GN)) != ARMNET_OK) return rc;
+    const int w_box = getenv("ARMNET_GEMM_1CTA") != nullptr ? GN : GN / 2;  // the pair kernel loads W in halves
+    if ((rc = make_map(&mh, w_hi, N, K, w_box)) != ARMNET_OK) return rc;
+    if ((rc = make_map(&ml, w_lo, N, K, w_box)) != ARMNET_OK) return rc;
     GemmParams P;
     P.out = partials;
     P.M = (int)B;
@@ -566,10 +776,17 @@ int armnet_mlp_linear_tf32x3(const float *x, int64_t B, int K, const float *w_hi
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         ARMNET_CUDA_TRY(cudaFuncSetAttribute(mlp_gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              G_SMEM_BYTES));
+        ARMNET_CUDA_TRY(cudaFuncSetAttribute(mlp_gemm_tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             G2_SMEM_BYTES));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    dim3 grid((unsigned)((B + GM - 1) / GM), (unsigned)((N + GN - 1) / GN), (unsigned)splits);
-    mlp_gemm_tf32x3_kernel<<<grid, G_THREADS, G_SMEM_BYTES, (cudaStream_t)stream>>>(mx, mh, ml, P);
+    if (getenv("ARMNET_GEMM_1CTA") != nullptr) {  // tuning experiments only: the single-CTA (cta_group::1) kernel
+        dim3 grid((unsigned)((B + GM - 1) / GM), (unsigned)((N + GN - 1) / GN), (unsigned)splits);
+        mlp_gemm_tf32x3_kernel<<<grid, G_THREADS, G_SMEM_BYTES, (cudaStream_t)stream>>>(mx, mh, ml, P);
+    } else {
+        dim3 grid((unsigned)(2 * ((B + 2 * GM - 1) / (2 * GM))), (unsigned)((N + GN - 1) / GN), (unsigned)splits);
+        mlp_gemm_tf32x3_pair_kernel<<<grid, G_THREADS, G2_SMEM_BYTES, (cudaStream_t)stream>>>(mx, mh, ml, P);
+    }
     ARMNET_CUDA_TRY(cudaGetLastError());
     note_launches(1);
     return ARMNET_OK;
