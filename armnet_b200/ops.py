@@ -10,7 +10,7 @@ import torch
 from . import _capi
 from ._capi import SOLVER_AUTO, SOLVER_BISECT, check, lib
 
-__all__ = ['partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
+__all__ = ['clamp_adam', 'partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
            'SOLVER_AUTO', 'SOLVER_BISECT', 'last_launch_count']
 
 
@@ -333,3 +333,15 @@ def mlp_tail(partials, packed, n_rest, noutput, B):
     check(lib.armnet_mlp_tail_f32(partials.data_ptr(), S, B, H, n_rest, noutput, packed.data_ptr(), y.data_ptr(),
                                   _stream()), 'armnet_mlp_tail_f32')
     return y
+
+
+def clamp_adam(param, grad, exp_avg, exp_avg_sq, grad_scale, clamp, lr, beta1, beta2, eps, step):
+    """armnet_clamp_adam_f32: in-place dense Adam over flat fp32 buffers, fused with gradient scaling and clamping."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    n = param.numel()
+    assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    check(lib.armnet_clamp_adam_f32(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,
+                                    float(grad_scale), float(clamp if clamp is not None else 0.0), float(lr), float(beta1),
+                                    float(beta2), float(eps), int(step), _stream()), 'armnet_clamp_adam_f32')

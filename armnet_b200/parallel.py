@@ -66,6 +66,54 @@ class GradAllReducer:
             p.grad = v                                        # optimizer reads straight from the bucket
 
 
+class FlatAdam:
+    """Dense Adam for data-parallel training on ONE flat parameter buffer (train.py:62-65 semantics).
+
+    The parameters are re-pointed to views of a flat fp32 buffer and their .grad to views of a flat gradient bucket, so
+    autograd accumulates straight into the bucket and step() is: [one NCCL all-reduce(sum) of the bucket] -> ONE kernel
+    (armnet_clamp_adam_f32) that averages, clamps to [-clamp, clamp] and applies the Adam update in a single pass over
+    (p, g, m, v).  Equivalent to GradAllReducer.step() + torch.optim.Adam.step()."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, clamp=1.0, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.lr, self.betas, self.eps, self.clamp, self.group = lr, betas, eps, clamp, group
+        dev = self.params[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('FlatAdam runs on CUDA parameters only (armnet_b200 has no CPU path)')
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]           # every view starts 16-byte aligned
+        n = sum(sizes)
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.t = 0
+        off = 0
+        with torch.no_grad():
+            for p, sz in zip(self.params, sizes):
+                view = self.flat_p[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+                p.grad = self.flat_g[off:off + p.numel()].view_as(p)
+                off += sz
+
+    def numel(self):
+        return self.flat_p.numel()
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    @torch.no_grad()
+    def step(self, weight=1.0):
+        """`weight` as in GradAllReducer.step (this rank's share of the global batch times world size)."""
+        from . import ops
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+        self.t += 1
+        ops.clamp_adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, weight / world, self.clamp, self.lr,
+                       self.betas[0], self.betas[1], self.eps, self.t)
+
+
 @torch.no_grad()
 def broadcast_buffers(model: torch.nn.Module, src: int = 0, group=None) -> None:
     """BatchNorm running statistics are per-replica in DP (the reference has no SyncBN); make them rank `src`'s

@@ -155,6 +155,18 @@ size_t armnet_mlp_tail_packed_floats(int H, int n_rest, int NO);
 int armnet_mlp_tail_f32(const float *partials, int splits, int64_t B, int H, int n_rest, int NO, const float *packed,
                         float *y, void *stream);
 
+/*
+ * Dense Adam over a flat fp32 bucket fused with gradient averaging and the [-clamp, clamp] gradient clamp of the
+ * reference's per-parameter hooks (train.py:62-65: optim.Adam(lr), p.register_hook(g.clamp(-1, 1))):
+ *     g = clamp(grad * grad_scale, -clamp, clamp)            (clamp <= 0: no clamp; grad_scale = 1 / world size)
+ *     m = lerp(m, g, 1 - beta1);  v = beta2 v + (1 - beta2) g^2
+ *     p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)        (torch.optim.Adam, no amsgrad)
+ * step is the 1-based update count.  One pass over (p, g, m, v); buffers 16-byte aligned.
+ */
+int armnet_clamp_adam_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                          float grad_scale, float clamp, float lr, float beta1, float beta2, float eps, int64_t step,
+                          void *stream);
+
 /* Number of kernels the last armnet_fused_fwd_f32 call on this thread launched (bench bookkeeping). */
 int armnet_last_launch_count(void);
 
