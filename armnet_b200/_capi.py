@@ -34,6 +34,9 @@ SIGNATURES = {
     'armnet_mlp_linear_tf32x3': (_I, [_P, _L, _I, _P, _P, _I, _I, _P, _P]),
     'armnet_mlp_tail_packed_floats': (_Z, [_I, _I, _I]),
     'armnet_mlp_tail_f32': (_I, [_P, _I, _L, _I, _I, _I, _P, _P, _P]),
+    'armnet_bn_workspace_floats': (_Z, [_L, _I, _I]),
+    'armnet_bn_train_fwd_f32': (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
+    'armnet_bn_train_bwd_f32': (_I, [_P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'armnet_clamp_adam_f32': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _L, _P]),
     'armnet_fused_fwd_f32': (_I, [_P, _I, _P, _P, _L, _L, _P, _P, _P, _I, _F, _I, _I, _L, _I, _I, _I, _I, _I,
                                   _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -81,6 +81,7 @@ class ARMNetModel(nn.Module):
         self.solver = ops.SOLVER_AUTO
         self.fuse_bn = True          # eval mode: apply arm_bn in the kernel epilogue
         self.fused_backward = True   # training: fused backward kernel (else unfused autograd stages)
+        self.cuda_bn = True          # training: arm_bn batch statistics by csrc/bn.cu (else nn.BatchNorm1d / cuDNN)
         self._shadow = _PaddedTable()
         self._err_flag = None
         self._bn_key = None
@@ -137,6 +138,15 @@ class ARMNetModel(nn.Module):
         z = torch.exp(torch.einsum('bfe,bkof->bkoe', e, w))
         return z.reshape(z.shape[0], -1, z.shape[-1])
 
+    def _arm_bn(self, z):
+        """arm_bn (armnet.py:89) outside the kernel epilogue: batch statistics (train mode) run in the streaming kernels
+        of csrc/bn.cu (cuDNN's kernel for this [B, K*O, nemb] layout takes 0.7 ms at the Criteo shape); anything else
+        (eval without fusion) is the stock module."""
+        bn = self.arm_bn
+        if self.cuda_bn and (bn.training or not bn.track_running_stats) and z.is_cuda and z.dtype == torch.float32:
+            return ops.batch_norm_train(z, bn)
+        return bn(z)
+
     def _needs_grad(self):
         return torch.is_grad_enabled() and (self.embedding.embedding.weight.requires_grad or
                                             any(p.requires_grad for p in self.attn_layer.parameters()))
@@ -147,9 +157,9 @@ class ARMNetModel(nn.Module):
             raise RuntimeError('armnet_b200.ARMNetModel runs on CUDA only (no CPU fallback): move the model and the '
                                'batch to a B200')
         if self._needs_grad():
-            x_arm = self.arm_bn(self._interaction_autograd(x))
+            x_arm = self._arm_bn(self._interaction_autograd(x))
         elif self.arm_bn.training or not self.arm_bn.track_running_stats or not self.fuse_bn:
-            x_arm = self.arm_bn(self.interaction(x))
+            x_arm = self._arm_bn(self.interaction(x))
         else:
             x_arm = self.interaction(x, fold_bn=True)     # eval: BatchNorm is a per-neuron affine, fused
         B = x_arm.shape[0]

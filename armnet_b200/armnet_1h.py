@@ -58,6 +58,7 @@ class ARMNetModel(_MultiHead):
         self.solver = ops.SOLVER_AUTO
         self.fuse_bn = True
         self.fused_backward = True
+        self.cuda_bn = True
         self._shadow = _PaddedTable()
         self._err_flag = None
         self._bn_key = None

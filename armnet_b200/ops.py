@@ -10,7 +10,7 @@ import torch
 from . import _capi
 from ._capi import SOLVER_AUTO, SOLVER_BISECT, check, lib
 
-__all__ = ['clamp_adam', 'partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
+__all__ = ['batch_norm_train', 'clamp_adam', 'partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
            'SOLVER_AUTO', 'SOLVER_BISECT', 'last_launch_count']
 
 
@@ -345,3 +345,56 @@ def clamp_adam(param, grad, exp_avg, exp_avg_sq, grad_scale, clamp, lr, beta1, b
     check(lib.armnet_clamp_adam_f32(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n,
                                     float(grad_scale), float(clamp if clamp is not None else 0.0), float(lr), float(beta1),
                                     float(beta2), float(eps), int(step), _stream()), 'armnet_clamp_adam_f32')
+
+
+# ---------------------------------------------------------------------------------------------- train-mode arm_bn
+class _BatchNormTrainFn(torch.autograd.Function):
+    """F.batch_norm(x [B,C,L], training=True) with the CUDA kernels of csrc/bn.cu (armnet.py:89 in train mode)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps):
+        _need_cuda(x)
+        x = _f32c(x, 'x')
+        B, C, L = x.shape
+        ws = torch.empty(lib.armnet_bn_workspace_floats(B, C, L), dtype=torch.float32, device=x.device)
+        out = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        rc = lib.armnet_bn_train_fwd_f32(
+            x.data_ptr(), B, C, L, weight.data_ptr() if weight is not None else None,
+            bias.data_ptr() if bias is not None else None,
+            running_mean.data_ptr() if running_mean is not None else None,
+            running_var.data_ptr() if running_var is not None else None, float(momentum), float(eps), out.data_ptr(),
+            mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), _stream())
+        if rc == -2:
+            raise ValueError(f'Expected more than 1 value per channel when training, got input size {tuple(x.shape)}')
+        check(rc, 'armnet_bn_train_fwd_f32')
+        ctx.save_for_backward(x, weight, mean, invstd)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, invstd = ctx.saved_tensors
+        dy = _f32c(dy, 'dy')
+        B, C, L = x.shape
+        ws = torch.empty(lib.armnet_bn_workspace_floats(B, C, L), dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        dw = torch.empty(C, dtype=torch.float32, device=x.device)
+        db = torch.empty(C, dtype=torch.float32, device=x.device)
+        check(lib.armnet_bn_train_bwd_f32(x.data_ptr(), dy.data_ptr(), B, C, L,
+                                          weight.data_ptr() if weight is not None else None, mean.data_ptr(),
+                                          invstd.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                          _stream()), 'armnet_bn_train_bwd_f32')
+        return dx, (dw if weight is not None else None), (db if weight is not None else None), None, None, None, None
+
+
+def batch_norm_train(x, bn):
+    """Train-mode forward of an nn.BatchNorm1d module `bn` on x [B,C,L] (statistics over B and L), including the
+    running-statistics update and num_batches_tracked, through armnet_bn_train_fwd_f32 / _bwd_f32."""
+    momentum = bn.momentum
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
+    return _BatchNormTrainFn.apply(x, bn.weight, bn.bias, rm, rv, 0.0 if momentum is None else momentum, bn.eps)

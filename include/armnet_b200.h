@@ -156,6 +156,24 @@ int armnet_mlp_tail_f32(const float *partials, int splits, int64_t B, int H, int
                         float *y, void *stream);
 
 /*
+ * Train-mode arm_bn = nn.BatchNorm1d(K*O) on the interaction output x [B, C, L] (models/armnet.py:67,89,
+ * armnet_1h.py:65,85): batch statistics per channel over (B, L), torch semantics (normalise with the biased variance,
+ * running_var updated with the unbiased one, running = (1 - momentum) running + momentum batch).
+ *   fwd: out = (x - mean) * invstd * weight + bias; save_mean / save_invstd [C] for the backward; running_* may be NULL.
+ *   bwd: dx, dweight = sum dy * xhat, dbias = sum dy (what autograd derives for F.batch_norm(training=True)).
+ * weight / bias may be NULL (affine=False).  workspace: armnet_bn_workspace_floats(B, C, L) floats.
+ * Sums are taken around a per-channel pivot and combined in a fixed order in double: deterministic, and free of the
+ * E[x^2] - E[x]^2 cancellation that x = exp(s) ~ 1 would cause.  Three launches each.
+ */
+size_t armnet_bn_workspace_floats(int64_t B, int C, int L);
+int armnet_bn_train_fwd_f32(const float *x, int64_t B, int C, int L, const float *weight, const float *bias,
+                            float *running_mean, float *running_var, float momentum, float eps, float *out,
+                            float *save_mean, float *save_invstd, float *workspace, void *stream);
+int armnet_bn_train_bwd_f32(const float *x, const float *dy, int64_t B, int C, int L, const float *weight,
+                            const float *save_mean, const float *save_invstd, float *dx, float *dweight, float *dbias,
+                            float *workspace, void *stream);
+
+/*
  * Dense Adam over a flat fp32 bucket fused with gradient averaging and the [-clamp, clamp] gradient clamp of the
  * reference's per-parameter hooks (train.py:62-65: optim.Adam(lr), p.register_hook(g.clamp(-1, 1))):
  *     g = clamp(grad * grad_scale, -clamp, clamp)            (clamp <= 0: no clamp; grad_scale = 1 / world size)

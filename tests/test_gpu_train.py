@@ -57,3 +57,48 @@ def test_flat_adam_trains_the_drop_in_model():
         fa.step()
         losses.append(loss.item())
     assert losses[-1] < 0.7 * losses[0]
+
+
+@pytest.mark.parametrize('B,C,L', [(4096, 512, 16), (257, 40, 10), (64, 3, 1), (2, 7, 5)])
+def test_train_mode_arm_bn_matches_torch(B, C, L):
+    """csrc/bn.cu against nn.BatchNorm1d in train mode: output, running statistics, dx / dweight / dbias."""
+    from armnet_b200 import ops
+    torch.manual_seed(B + C)
+    # like the interaction output at initialisation: exp(small) ~ 1 with a tiny spread (cancellation-prone)
+    z = torch.exp(torch.randn(B, C, L, device=dev()) * 1e-3 + torch.randn(1, C, 1, device=dev()) * 0.05)
+    ref = nn.BatchNorm1d(C).to(dev()).train()
+    ours = nn.BatchNorm1d(C).to(dev()).train()
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5)
+        ref.bias.normal_(0, 0.3)
+        ours.load_state_dict(ref.state_dict())
+    z1 = z.clone().requires_grad_(True)
+    z2 = z.clone().requires_grad_(True)
+    y1 = ref(z1.double()).float() if False else ref(z1)
+    y2 = ops.batch_norm_train(z2, ours)
+    # fp64 evaluation is the judge: our error must not exceed cuDNN's by much
+    z64 = z.double()
+    m64 = z64.mean(dim=(0, 2), keepdim=True)
+    v64 = z64.var(dim=(0, 2), unbiased=False, keepdim=True)
+    y64 = (z64 - m64) / torch.sqrt(v64 + ref.eps) * ref.weight.double().view(1, C, 1) + ref.bias.double().view(1, C, 1)
+    e_ref = (y1.double() - y64).abs().max().item()
+    e_ours = (y2.double() - y64).abs().max().item()
+    print(f'B={B} C={C} L={L}: max abs err vs fp64: ours {e_ours:.2e}, torch/cuDNN {e_ref:.2e}')
+    assert e_ours <= max(2 * e_ref, 1e-4)
+    assert torch.allclose(ours.running_mean, ref.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ours.running_var, ref.running_var, rtol=1e-4, atol=1e-7)
+    assert int(ours.num_batches_tracked) == 1
+    gy = torch.randn(B, C, L, device=dev())
+    y1.backward(gy)
+    y2.backward(gy)
+    scale = z1.grad.abs().max().item()
+    assert (z2.grad - z1.grad).abs().max().item() <= 2e-3 * scale
+    assert torch.allclose(ours.weight.grad, ref.weight.grad, rtol=2e-3, atol=2e-3 * ref.weight.grad.abs().max().item())
+    assert torch.allclose(ours.bias.grad, ref.bias.grad, rtol=1e-4, atol=1e-4 * ref.bias.grad.abs().max().item())
+
+
+def test_train_mode_bn_single_value_raises():
+    from armnet_b200 import ops
+    bn = nn.BatchNorm1d(4).to(dev()).train()
+    with pytest.raises(ValueError):
+        ops.batch_norm_train(torch.ones(1, 4, 1, device=dev()), bn)
