@@ -8,7 +8,8 @@ from .entmax import EntmaxBisect, entmax_bisect
 from .layers import MLP, Embedding
 from .model_utils import create_model
 from .serving import BatchScorer
+from . import zoo
 
 __all__ = ['ARMNetModel', 'ARMNet1H', 'SparseAttLayer', 'SparseAttention', 'EntmaxBisect', 'entmax_bisect',
-           'Embedding', 'MLP', 'create_model', 'BatchScorer', 'ops']
+           'Embedding', 'MLP', 'create_model', 'BatchScorer', 'ops', 'zoo']
 __version__ = '0.1.0'

@@ -23,6 +23,7 @@ SIGNATURES = {
     'armnet_last_launch_count': (_I, []),
     'armnet_device_info': (_I, [C.POINTER(_I), C.POINTER(_I)]),
     'armnet_embed_gather_f32': (_I, [_P, _I, _P, _P, _L, _L, _L, _I, _I, _P, _I, _F, _F, _I, _P, _P]),
+    'armnet_linear_gather_f32': (_I, [_P, _I, _P, _P, _L, _L, _I, _P, _P, _P, _P]),
     'armnet_entmax_f32': (_I, [_P, _L, _I, _F, _I, _I, _P, _P]),
     'armnet_entmax_bwd_f32': (_I, [_P, _P, _L, _I, _F, _P, _P]),
     'armnet_fused_workspace_bytes': (_Z, [_I, _I, _I, _I]),

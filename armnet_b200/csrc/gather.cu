@@ -103,3 +103,60 @@ extern "C" int armnet_embed_gather_f32(const void *ids, int ids_i32, float *valu
     note_launches(1);
     return ARMNET_OK;
 }
+
+// armnet_linear_gather_f32: layers.Linear.forward (models/layers.py:31-37), the 1-wide embedding of the LR term used by
+// the zoo models (afm.py:40, xdfm.py:46,67):  y[b] = sum_f weight[ids[b,f]] * values[b,f] + bias.
+// One warp per sample: lanes stride over the fields (coalesced id / value reads), shuffle tree for the sum.
+namespace armnet {
+template <bool I32>
+__global__ void __launch_bounds__(256) linear_gather_kernel(const void *__restrict__ ids_, const float *__restrict__ values,
+                                                            const float *__restrict__ weight, long long V, long long B,
+                                                            int F, const float *__restrict__ bias, float *__restrict__ y,
+                                                            int *__restrict__ err_flag) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+        float acc = 0.f;
+        for (int f = lane; f < F; f += 32) {
+            const long long id = I32 ? (long long)reinterpret_cast<const int *>(ids_)[b * F + f]
+                                     : reinterpret_cast<const long long *>(ids_)[b * F + f];
+            if ((unsigned long long)id >= (unsigned long long)V) {
+                if (err_flag) atomicOr(err_flag, 1);
+            } else {
+                acc = fmaf(__ldg(weight + id), __ldg(values + b * F + f), acc);
+            }
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+        if (lane == 0) y[b] = acc + (bias ? __ldg(bias) : 0.f);
+    }
+}
+}  // namespace armnet
+
+extern "C" int armnet_linear_gather_f32(const void *ids, int ids_i32, const float *values, const float *weight, int64_t V,
+                                        int64_t B, int F, const float *bias, float *y, int *err_flag, void *stream) {
+    using namespace armnet;
+    note_launches(0);
+    if (B == 0) return ARMNET_OK;
+    if (!ids || !values || !weight || !y) {
+        set_error("linear_gather: null pointer");
+        return ARMNET_ERR_NULL;
+    }
+    if (V <= 0 || B < 0 || F <= 0) {
+        set_error("linear_gather: bad shape V=%lld B=%lld F=%d", (long long)V, (long long)B, F);
+        return ARMNET_ERR_SHAPE;
+    }
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc != ARMNET_OK) return rc;
+    long long blocks = (B * 32 + 255) / 256;
+    const long long cap = (long long)di.sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (ids_i32)
+        linear_gather_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ids, values, weight, V, B, F, bias, y, err_flag);
+    else
+        linear_gather_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ids, values, weight, V, B, F, bias, y, err_flag);
+    ARMNET_CUDA_TRY(cudaGetLastError());
+    note_launches(1);
+    return ARMNET_OK;
+}

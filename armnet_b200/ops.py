@@ -10,7 +10,7 @@ import torch
 from . import _capi
 from ._capi import SOLVER_AUTO, SOLVER_BISECT, check, lib
 
-__all__ = ['batch_norm_train', 'clamp_adam', 'partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
+__all__ = ['linear_gather', 'batch_norm_train', 'clamp_adam', 'partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
            'SOLVER_AUTO', 'SOLVER_BISECT', 'last_launch_count']
 
 
@@ -398,3 +398,18 @@ def batch_norm_train(x, bn):
             momentum = 1.0 / float(bn.num_batches_tracked)
     rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
     return _BatchNormTrainFn.apply(x, bn.weight, bn.bias, rm, rv, 0.0 if momentum is None else momentum, bn.eps)
+
+
+def linear_gather(ids, values, weight, bias=None, err_flag=None):
+    """layers.Linear.forward (layers.py:31-37): y[b] = sum_f weight[ids[b,f]] * values[b,f] + bias. weight [V,1] or [V]."""
+    _need_cuda(ids, values, weight)
+    ids_c = ids.contiguous()
+    values = _f32c(values, 'values')
+    w = _f32c(weight.detach(), 'weight').reshape(-1)
+    B, F = ids_c.shape
+    y = torch.empty(B, dtype=torch.float32, device=w.device)
+    check(lib.armnet_linear_gather_f32(ids_c.data_ptr(), _ids_arg(ids_c), values.data_ptr(), w.data_ptr(), w.numel(), B, F,
+                                       bias.data_ptr() if bias is not None else None, y.data_ptr(),
+                                       err_flag.data_ptr() if err_flag is not None else None, _stream()),
+          'armnet_linear_gather_f32')
+    return y

@@ -60,6 +60,14 @@ int armnet_embed_gather_f32(const void *ids, int ids_i32, float *values, const f
                             float clamp_hi, int clamp_inplace, int *err_flag, void *stream);
 
 /*
+ * layers.Linear.forward (models/layers.py:31-37): the 1-wide embedding of the LR term the zoo models add
+ * (afm.py:40, xdfm.py:46,67):  y[b] = sum_f weight[ids[b,f]] * values[b,f] + bias[0]   (bias may be NULL).
+ * weight: [V] (the nn.Embedding(nfeat, 1) parameter), y: [B].
+ */
+int armnet_linear_gather_f32(const void *ids, int ids_i32, const float *values, const float *weight, int64_t V,
+                             int64_t B, int F, const float *bias, float *y, int *err_flag, void *stream);
+
+/*
  * EntmaxBisect.forward / entmax_bisect / nn.Softmax(dim=-1) over the last axis
  * (utils/entmax.py:238-275, :134-175, :29-68; models/armnet.py:12-13).  x, p: [rows, F].
  */
