@@ -38,6 +38,8 @@ SIGNATURES = {
     'armnet_bn_workspace_floats': (_Z, [_L, _I, _I]),
     'armnet_bn_train_fwd_f32': (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
     'armnet_bn_train_bwd_f32': (_I, [_P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'armnet_libsvm_count_lines': (_I, [C.c_char_p, C.POINTER(_L)]),
+    'armnet_libsvm_parse': (_I, [C.c_char_p, _I, _L, _P, _P, _P, C.POINTER(_L), C.POINTER(_L)]),
     'armnet_clamp_adam_f32': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _L, _P]),
     'armnet_fused_fwd_f32': (_I, [_P, _I, _P, _P, _L, _L, _P, _P, _P, _I, _F, _I, _I, _L, _I, _I, _I, _I, _I,
                                   _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

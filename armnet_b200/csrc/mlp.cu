@@ -378,6 +378,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
     if (warp == 1) tmem_alloc_pair(tmem_slot, 2 * GN);
     tc_fence_before();
     cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals across the pair
+    __syncthreads();     // (redundant after the cluster barrier; compute-sanitizer's racecheck only models CTA barriers)
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
 

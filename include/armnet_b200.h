@@ -193,6 +193,16 @@ int armnet_clamp_adam_f32(float *param, const float *grad, float *exp_avg, float
                           float grad_scale, float clamp, float lr, float beta1, float beta2, float eps, int64_t step,
                           void *stream);
 
+/*
+ * Input pipeline (HOST functions, host pointers): libsvm text (`label id:val id:val ...`, data_loader.py:12-47) -> dense
+ * [N, nfield] arrays.  armnet_libsvm_count_lines gives an upper bound for N; armnet_libsvm_parse fills ids (int32),
+ * values, labels for every well-formed line (exactly nfield `id:val` pairs) and counts the skipped ones, like the
+ * reference's per-line try/except (data_loader.py:37-44).  armnet_b200/data.py caches the result as raw binary files.
+ */
+int armnet_libsvm_count_lines(const char *path, int64_t *n_lines);
+int armnet_libsvm_parse(const char *path, int nfield, int64_t capacity, int32_t *ids, float *values, float *labels,
+                        int64_t *n_rows, int64_t *n_skipped);
+
 /* Number of kernels the last armnet_fused_fwd_f32 call on this thread launched (bench bookkeeping). */
 int armnet_last_launch_count(void);
 

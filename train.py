@@ -18,6 +18,7 @@ import os
 import sys
 import time
 
+import numpy as np
 import torch
 from torch import nn, optim
 
@@ -59,30 +60,20 @@ def get_args(argv=None):
     p.add_argument('--seed', type=int, default=2025, help='seed for reproducibility')
     p.add_argument('--repeat', type=int, default=1, help='number of repeats with seeds [seed, seed+repeat)')
     p.add_argument('--synthetic_rows', type=int, default=200000, help='rows of the synthetic training split')
+    p.add_argument('--host_data', action='store_true',
+                   help='keep the splits in host memory and copy every batch (default: whole splits resident in HBM, '
+                        'batches cut on the device, armnet_b200/data.py)')
     return p.parse_args(argv)
 
 
 # ------------------------------------------------------------------------------------------------ data
 
 def load_libsvm(path, nfield):
-    """`label id:val id:val ...` per line -> (id [N,F] int64, value [N,F] f32, y [N] f32); malformed lines are
-    skipped like data_loader.py:37-44."""
-    ids, vals, ys = [], [], []
-    with open(path) as f:
-        for line in f:
-            parts = line.split()
-            if len(parts) != nfield + 1:
-                continue
-            try:
-                pairs = [t.split(':') for t in parts[1:]]
-                row = ([int(a) for a, _ in pairs], [float(b) for _, b in pairs], float(parts[0]))
-            except ValueError:
-                continue
-            ids.append(row[0])
-            vals.append(row[1])
-            ys.append(row[2])
-    return (torch.tensor(ids, dtype=torch.int64), torch.tensor(vals, dtype=torch.float32),
-            torch.tensor(ys, dtype=torch.float32))
+    """`label id:val id:val ...` per line -> (id [N,F] int32, value [N,F] f32, y [N] f32) through the native parser and
+    its binary cache (armnet_b200/data.py); malformed lines are skipped like data_loader.py:37-44."""
+    from armnet_b200.data import load_split
+    ids, vals, y = load_split(path, nfield)
+    return (torch.from_numpy(np.array(ids)), torch.from_numpy(np.array(vals)), torch.from_numpy(np.array(y)))
 
 
 def synthetic_split(n, nfield, nfeat, seed):
@@ -153,10 +144,19 @@ def run(epoch, model, split, args, plogger, dev, rank, world, optimizer=None, re
     time_avg, loss_avg, auc_avg = Meter(), Meter(), Meter()
     stamp = time.time()
     gen = torch.Generator().manual_seed(args.seed * 1000 + epoch)       # same shuffle on every rank
-    n_batches = (split[2].shape[0] + args.batch_size - 1) // args.batch_size
-    for bi, batch in enumerate(batches(split, args.batch_size, optimizer is not None, gen)):
-        full_n = batch['y'].shape[0]
-        mine = shard_batch(batch, rank, world) if (world > 1 and optimizer) else batch
+    from armnet_b200.data import DeviceSplit
+    if isinstance(split, DeviceSplit):      # batches are cut (and sharded) on the device
+        it = split.batches(args.batch_size, optimizer is not None, gen, rank, world if optimizer else 1)
+        n_rows = len(split)
+    else:
+        it = batches(split, args.batch_size, optimizer is not None, gen)
+        n_rows = split[2].shape[0]
+    for bi, batch in enumerate(it):
+        if isinstance(split, DeviceSplit):
+            full_n, mine = batch['global_rows'], batch
+        else:
+            full_n = batch['y'].shape[0]
+            mine = shard_batch(batch, rank, world) if (world > 1 and optimizer) else batch
         x = {'id': mine['id'].to(dev, non_blocking=True), 'value': mine['value'].to(dev, non_blocking=True)}
         target = mine['y'].to(dev, non_blocking=True)
         if optimizer:
@@ -175,7 +175,7 @@ def run(epoch, model, split, args, plogger, dev, rank, world, optimizer=None, re
         time_avg.update(time.time() - stamp)
         stamp = time.time()
         if bi % args.report_freq == 0 and rank == 0:
-            plogger.info(f'Epoch [{epoch:3d}/{args.epoch}][{bi:3d}/{n_batches}]\t{time_avg.val:.3f} ({time_avg.avg:.3f}) '
+            plogger.info(f'Epoch [{epoch:3d}/{args.epoch}][{bi:3d}/{(n_rows + args.batch_size - 1) // args.batch_size}]\t{time_avg.val:.3f} ({time_avg.avg:.3f}) '
                          f'AUC {auc_avg.val:4f} ({auc_avg.avg:4f}) Loss {loss_avg.val:8.4f} ({loss_avg.avg:8.4f})')
         if bi >= args.eval_freq:
             break
@@ -194,6 +194,10 @@ def main(args, data, rank, world, dev):
     if rank == 0:
         plogger.handlers.append(logging.FileHandler(os.path.join(args.log_dir, args.exp_name, 'stdout.log')))
     model = ab.create_model(args, plogger).to(dev)
+    if not args.host_data:
+        from armnet_b200.data import DeviceSplit
+        data = [DeviceSplit(*split, device=dev) for split in data]
+        plogger.info(f'splits resident on {dev}: {sum(d.nbytes() for d in data) / 1e6:.1f} MB')
     plogger.info(vars(args))
     optimizer = optim.Adam(model.parameters(), lr=args.lr)              # dense Adam over every parameter (train.py:62)
     reducer = GradAllReducer(model.parameters(), clamp=1.0)
