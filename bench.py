@@ -50,6 +50,10 @@ WORKLOADS = {
 # capture (profiles/r1_v5_summary.md, r1_v5_fwd_ncu.txt): 21.82 MB read + 25.13 MB written. Below the algorithmic 92.2 MB because part
 # of the 84 MB output is still dirty in the 126 MB L2 when the kernel ends; no re-reads.
 NCU_TRAFFIC_BYTES = {'c2a': 46956288}
+# FP32-pipe lane-cycles per (sample, neuron) row of armnet_fwd_kernel<39,1,10,1> from the same capture's executed-opcode
+# histogram (profiles/r1_v5_fwd_ncu.txt): FFMA2 409.5, FADD2 98, FMUL2 64 (2 pipe cycles each) + FADD 53, FFMA 44, FMUL 16.5.
+# Used for the honest second ceiling: the path is FP32-issue bound, not HBM bound.
+NCU_FP32_PIPE_CYCLES_PER_ROW = {'c2a': 2 * (409.5 + 98.0 + 64.0) + 53.0 + 44.0 + 16.5}
 METRIC = 'CTR samples/sec (bsz=4096, Criteo-shape) at 1/2/4/8 B200; HBM GB/s vs roofline'
 
 
@@ -309,6 +313,14 @@ def main():
     peak, peak_src = peaks()
     abytes = algorithmic_bytes_per_sample(w) * w['bsz']
     achieved = abytes / (ms_per_step * 1e-3) / 1e9        # per GPU: one launch processes one batch
+    fp32_pipe = None
+    if args.workload in NCU_FP32_PIPE_CYCLES_PER_ROW and clocks and clocks.get('sm_mhz'):
+        # warp-level FP32-pipe cycles the kernel needs per second / what 148 SMs x 4 sub-partitions offer at the sampled clock
+        rows_per_s = value / n * w['nhead'] * w['nhid']
+        need = rows_per_s / 32.0 * NCU_FP32_PIPE_CYCLES_PER_ROW[args.workload]   # one warp instruction serves 32 row-threads
+        have = 148 * 4 * clocks['sm_mhz'] * 1e6
+        fp32_pipe = {'frac': need / have, 'what': 'FMA-pipe busy fraction implied by the measured rate and the ncu '
+                     'opcode histogram (ncu direct: sm__pipe_fma_cycles_active 52.7 %)'}
     out = {
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': n, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
@@ -319,7 +331,8 @@ def main():
                      'traffic': NCU_TRAFFIC_BYTES.get(args.workload), 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': abytes,
                      'kernel': 'armnet_fwd_kernel (+ attn_prepare_kernel, ~1% of the step)',
-                     'note': 'path is FP32-issue/MUFU bound (entmax), not HBM bound; see DESIGN.md'},
+                     'note': 'path is FP32-issue/MUFU bound (entmax), not HBM bound; see DESIGN.md',
+                     'fp32_pipe': fp32_pipe},
         'e2e': {'value': w['bsz'] * args.steps * n / e2e_s, 'unit': 'samples/s',
                 'h2d_bytes_per_step': w['bsz'] * w['nfield'] * 12, 'd2h_bytes_per_step': w['bsz'] * 4,
                 'ms_per_step': e2e_s / args.steps * 1e3,
