@@ -296,6 +296,44 @@ def main():
     e2e_sync_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
+    # the MLP kernels of the e2e step, timed alone (CUDA events, warm L2: in the pipeline their input was just written)
+    mlp_info = None
+    with torch.no_grad():
+        mlp_fast = model.mlp._fast_ok(torch.empty(2, model.mlp.ninput, device=dev))
+    if rank == 0 and mlp_fast:
+        with torch.no_grad():
+            x_mlp = model.interaction({'id': resident[0][0], 'value': resident[0][1]}, fold_bn=True).reshape(w['bsz'], -1)
+            w_hi, w_lo, packed = model.mlp._prepared()
+
+            def ev_time(fn, n=20):
+                for _ in range(3):
+                    fn()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(n):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) / n * 1e-3
+
+            t_gemm = ev_time(lambda: ops.mlp_first_linear(x_mlp, w_hi, w_lo))
+            part = ops.mlp_first_linear(x_mlp, w_hi, w_lo)
+            t_tail = ev_time(lambda: ops.mlp_tail(part, packed, model.mlp.nlayers - 1, model.mlp.noutput, w['bsz']))
+        flops = 3 * 2.0 * w['bsz'] * model.mlp.ninput * model.mlp.nhid         # three TF32 MMAs per fp32 product
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                tf32_peak = float(json.load(f)['bf16_tflops']) / 2.0           # TF32 runs at half the BF16 rate
+            src = 'MEASURED_PEAKS.json bf16_tflops / 2'
+        except Exception:
+            tf32_peak, src = 1125.0, 'nominal 2250 / 2'
+        mlp_info = {'gemm_kernel': 'mlp_gemm_tf32x3_pair_kernel (first Linear, 3xTF32 on tcgen05, cta_group::2)',
+                    'gemm_us': t_gemm * 1e6, 'gemm_tf32_tflops': flops / t_gemm / 1e12,
+                    'gemm_fp32_equivalent_tflops': flops / 3 / t_gemm / 1e12,
+                    'roofline': {'bound': 'tensor', 'achieved': flops / t_gemm / 1e12, 'peak': tf32_peak,
+                                 'unit': 'TFLOP/s', 'frac': flops / t_gemm / 1e12 / tf32_peak, 'peak_source': src},
+                    'tail_kernel_us': t_tail * 1e6}
+
     trained_like_(model)
     tab, ld = model._shadow.get(table) if model.padded_table else (table.detach(), table.shape[1])
     W, Q, Vv = (t.detach() for t in model._attn_weights())
@@ -345,6 +383,7 @@ def main():
         'trained_like': {'value': w['bsz'] * tl_steps * n / (tl_ms * 1e-3), 'unit': 'samples/s',
                          'what': 'same shapes, embedding~N(0,1), attention weights x4 (sparse gates)'},
         'step_ms_min_med_max': [min(per_step), statistics.median(per_step), max(per_step)],
+        'mlp': mlp_info,
         'clocks': clocks,
     }
     if rank == 0:
