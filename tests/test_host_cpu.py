@@ -120,3 +120,40 @@ def test_train_cli_surface_and_helpers(tmp_path):
     target = torch.tensor([0., 0., 1., 1.])
     assert abs(t.auc_on_device(logits, target) - 0.75) < 1e-12
     assert t.auc_on_device(logits, torch.ones(4)) == 0.0
+
+
+def test_argument_validation_of_mlp_training_and_data_entries_without_gpu():
+    """The newer entries also fail with error codes (never crash) before touching the device."""
+    from armnet_b200 import _capi
+    lib = _capi.lib
+    buf = ctypes.create_string_buffer(256)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.armnet_mlp_tail_packed_floats(256, 1, 1) == 2 * 256 + 256 * 256 + 2 * 256 + 256 + 1
+    assert lib.armnet_mlp_tail_packed_floats(0, 1, 1) == 0
+    assert lib.armnet_mlp_split_weight_f32(None, 8, p, p, None) == -1
+    assert lib.armnet_mlp_linear_tf32x3(None, 4, 8, p, p, 8, 1, p, None) == -1
+    assert lib.armnet_mlp_linear_tf32x3(p, 4, 8, p, p, 8, 0, p, None) == -2          # splits < 1
+    assert lib.armnet_mlp_linear_tf32x3(p, 4, 6, p, p, 8, 1, p, None) == -5          # K % 4 != 0: TMA cannot address rows
+    assert lib.armnet_mlp_tail_f32(p, 1, 4, 6, 0, 1, p, p, None) == -3               # H % 4 != 0
+    assert lib.armnet_mlp_tail_f32(p, 1, 4, 1024, 0, 1, p, p, None) == -3            # H > 512
+    assert lib.armnet_clamp_adam_f32(p, p, p, p, 16, 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 0, None) == -2   # step < 1
+    assert lib.armnet_clamp_adam_f32(None, p, p, p, 16, 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 1, None) == -1
+    assert lib.armnet_bn_train_fwd_f32(p, 1, 4, 1, None, None, None, None, 0.1, 1e-5, p, p, p, p, None) == -2
+    assert b'more than 1 value per channel' in lib.armnet_last_error_string()
+    assert lib.armnet_bn_workspace_floats(0, 4, 4) == 0
+    assert lib.armnet_linear_gather_f32(None, 0, p, p, 10, 4, 3, None, p, None, None) == -1
+    n = ctypes.c_int64(0)
+    assert lib.armnet_libsvm_count_lines(b'/nonexistent/file.libsvm', ctypes.byref(n)) == -2
+    assert b'cannot open' in lib.armnet_last_error_string()
+
+
+def test_training_helpers_refuse_cpu():
+    from armnet_b200.parallel import FlatAdam
+    from armnet_b200 import BatchScorer
+    import armnet_b200 as ab
+    lin = torch.nn.Linear(4, 2)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        FlatAdam(lin.parameters())
+    m = ab.ARMNetModel(10, 100, 10, 2, 1.7, 4, 1, 8, 0.0, False, 1, 8).eval()
+    with pytest.raises(RuntimeError, match='CUDA'):
+        BatchScorer(m, 8, 10)
