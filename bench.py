@@ -261,7 +261,7 @@ def main():
     # replays one CUDA graph per batch; every step's copies are inside the timed region.  (b) the plain module call with
     # a blocking read of y per batch (what train.py's eval loop does), reported next to it.
     from armnet_b200 import BatchScorer
-    scorer = BatchScorer(model, w['bsz'], w['nfield'], depth=2)
+    scorer = BatchScorer(model, w['bsz'], w['nfield'], depth=6, compute_streams=3)
 
     def e2e_pipelined(steps):
         pending, acc = [], 0.0
@@ -376,7 +376,8 @@ def main():
                 'ms_per_step': e2e_s / args.steps * 1e3,
                 'what': 'armnet_b200.BatchScorer over pinned host batches: H2D ids+values, full ARMNetModel forward '
                         '(fused kernel, tcgen05 MLP GEMM, tail kernel) as one CUDA graph per batch, D2H y; copies of '
-                        'batch i+1 overlap the forward of batch i',
+                        'batch i+1 overlap the forward of batch i; 6 slots on 3 compute streams (the GEMM / tail of one batch overlaps the '
+                        'fused kernel of the next)',
                 'per_call_sync': {'value': w['bsz'] * args.steps * n / e2e_sync_s, 'ms_per_step': e2e_sync_s / args.steps * 1e3,
                                   'what': 'y = model(batch_from_pinned_host).cpu() per batch, no overlap'}},
         'gpu_launches': launches,

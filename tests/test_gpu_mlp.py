@@ -89,8 +89,8 @@ def test_mlp_train_mode_uses_stock_path():
     assert m.mlp[0].weight.grad is not None
 
 
-@pytest.mark.parametrize('use_graph', [True, False])
-def test_batch_scorer_matches_module_forward(use_graph):
+@pytest.mark.parametrize('use_graph,depth,streams', [(True, 2, 1), (False, 2, 1), (True, 4, 2), (True, 6, 3)])
+def test_batch_scorer_matches_module_forward(use_graph, depth, streams):
     """serving.BatchScorer (pipelined copies, CUDA-graph replay) returns exactly what model(x) returns."""
     import armnet_b200 as ab
     torch.manual_seed(3)
@@ -98,12 +98,12 @@ def test_batch_scorer_matches_module_forward(use_graph):
     model = ab.ARMNetModel(F, V, 10, 4, 1.7, 32, 2, 64, 0.0, False, 2, 32).to(dev()).eval()
     g = torch.Generator().manual_seed(11)
     batches = [(torch.randint(0, V, (B, F), generator=g).pin_memory(),
-                (torch.rand(B, F, generator=g) * 1.3).pin_memory()) for _ in range(5)]
+                (torch.rand(B, F, generator=g) * 1.3).pin_memory()) for _ in range(13)]
     want = []
     with torch.no_grad():
         for ids, vals in batches:
             want.append(model({'id': ids.to(dev()), 'value': vals.clone().to(dev())}).cpu())
-    scorer = ab.BatchScorer(model, B, F, depth=2, use_graph=use_graph)
+    scorer = ab.BatchScorer(model, B, F, depth=depth, use_graph=use_graph, compute_streams=streams)
     got = list(scorer.score(batches))
     assert len(got) == len(want)
     for a, b in zip(got, want):
