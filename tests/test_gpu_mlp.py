@@ -111,3 +111,37 @@ def test_batch_scorer_matches_module_forward(use_graph, depth, streams):
     assert torch.equal(batches[0][1], batches[0][1].clone())     # host values are not clamped in place
     with pytest.raises(ValueError):
         scorer.submit(batches[0][0][:10], batches[0][1][:10])
+
+
+def test_full_size_eval_forward_matches_oracle():
+    """BASELINE config 2 at full size (39 fields, 1M vocabulary, nemb 10, 4 x 128 neurons, bsz 4096, mlp 2 x 256): the whole
+    eval forward -- fused kernel + arm_bn epilogue, tcgen05 GEMM, tail kernel -- through ARMNetModel.forward and through
+    BatchScorer, against the CPU oracle of the reference's forward on a sample of rows (samples are independent in eval
+    mode, armnet.py:82-101)."""
+    import armnet_b200 as ab
+    from oracle import armnet_oracle as oracle
+    F, V, E, K, O, B = 39, 1000000, 10, 4, 128, 4096
+    st = oracle.reference_init_state('armnet', F, V, E, K, O, mlp_nlayer=2, mlp_nhid=256, seed=2025)
+    g = torch.Generator().manual_seed(5)
+    st['embedding.embedding.weight'].normal_(0, 0.4, generator=g)        # trained-like: non-uniform gates
+    st['arm_bn.running_mean'].normal_(1.0, 0.2, generator=g)
+    st['arm_bn.running_var'].uniform_(0.5, 1.5, generator=g)
+    st['mlp.mlp.1.running_mean'].normal_(0, 0.2, generator=g)
+    st['mlp.mlp.1.running_var'].uniform_(0.5, 1.5, generator=g)
+    ids = torch.randint(0, V, (B, F), generator=g)
+    vals = torch.rand(B, F, generator=g) * 1.2
+    rows = torch.cat([torch.arange(0, 64), torch.arange(2000, 2064), torch.arange(B - 64, B)])
+    ref = oracle.forward(st, 1.7, ids[rows], vals[rows].clone())['y']
+    model = ab.ARMNetModel(F, V, E, K, 1.7, O, 2, 256, 0.0, False, 2, 256)
+    model.load_state_dict(st)
+    model = model.to(dev()).eval()
+    with torch.no_grad():
+        y = model({'id': ids.to(dev()), 'value': vals.clone().to(dev())}).cpu()
+    scale = max(ref.abs().max().item(), 1.0)
+    err = (y[rows] - ref).abs().max().item() / scale
+    scorer = ab.BatchScorer(model, B, F, depth=4, compute_streams=2)
+    t = scorer.submit(ids.pin_memory(), vals.pin_memory())
+    y2 = scorer.result(t).clone()
+    print(f'full-size eval forward: max |y - oracle| / scale = {err:.2e}')
+    assert err <= 2e-5
+    assert torch.equal(y2, y)                                             # same kernels, same results, graph or not

@@ -60,6 +60,9 @@ def get_args(argv=None):
     p.add_argument('--seed', type=int, default=2025, help='seed for reproducibility')
     p.add_argument('--repeat', type=int, default=1, help='number of repeats with seeds [seed, seed+repeat)')
     p.add_argument('--synthetic_rows', type=int, default=200000, help='rows of the synthetic training split')
+    p.add_argument('--torch_adam', action='store_true',
+                   help='torch.optim.Adam + separate gradient bucket (default: FlatAdam, one fused clamp+Adam kernel over '
+                        'a flat parameter / gradient bucket, armnet_b200/parallel.py)')
     p.add_argument('--host_data', action='store_true',
                    help='keep the splits in host memory and copy every batch (default: whole splits resident in HBM, '
                         'batches cut on the device, armnet_b200/data.py)')
@@ -162,10 +165,15 @@ def run(epoch, model, split, args, plogger, dev, rank, world, optimizer=None, re
         if optimizer:
             y = model(x)
             loss = crit(y.reshape(-1), target)
-            optimizer.zero_grad(set_to_none=True)
-            loss.backward()
-            reducer.step(weight=target.numel() * world / full_n)       # one all-reduce, then clamp (train.py:65)
-            optimizer.step()
+            if reducer is None:                                        # FlatAdam: bucket zero -> backward -> one
+                optimizer.zero_grad()                                  # all-reduce -> one fused clamp+Adam kernel
+                loss.backward()
+                optimizer.step(weight=target.numel() * world / full_n)
+            else:
+                optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+                reducer.step(weight=target.numel() * world / full_n)   # one all-reduce, then clamp (train.py:65)
+                optimizer.step()
         else:
             with torch.no_grad():
                 y = model(x)
@@ -199,8 +207,12 @@ def main(args, data, rank, world, dev):
         data = [DeviceSplit(*split, device=dev) for split in data]
         plogger.info(f'splits resident on {dev}: {sum(d.nbytes() for d in data) / 1e6:.1f} MB')
     plogger.info(vars(args))
-    optimizer = optim.Adam(model.parameters(), lr=args.lr)              # dense Adam over every parameter (train.py:62)
-    reducer = GradAllReducer(model.parameters(), clamp=1.0)
+    if args.torch_adam:
+        optimizer = optim.Adam(model.parameters(), lr=args.lr)          # dense Adam over every parameter (train.py:62)
+        reducer = GradAllReducer(model.parameters(), clamp=1.0)
+    else:
+        from armnet_b200.parallel import FlatAdam
+        optimizer, reducer = FlatAdam(model.parameters(), lr=args.lr, clamp=1.0), None   # train.py:62-65 in one kernel
     best_valid, best_test, patience = 0.0, 0.0, 0
     start = time.time()
     for epoch in range(args.epoch):
