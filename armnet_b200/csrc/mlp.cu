@@ -6,11 +6,15 @@
 // fp32 parity (the reference multiplies in fp32, layers.py:73) is kept with the 3xTF32 split:
 //     x = x_hi + x_lo,  w = w_hi + w_lo   (hi = fp32 rounded to the 10-bit TF32 mantissa, lo = exact remainder)
 //     x.w ~= x_hi.w_hi + x_lo.w_hi + x_hi.w_lo          (dropped x_lo.w_lo ~ 2^-22 relative)
-// three kind::tf32 MMAs per K step into the same fp32 TMEM accumulator.  w_hi / w_lo are split once per weight
+// three kind::tf32 MMAs per K step, the dominant term and the two corrections in separate fp32 TMEM accumulators
+// (the tensor core rounds each accumulation towards zero).  w_hi / w_lo are split once per weight
 // version (armnet_mlp_split_weight_f32); x is split in shared memory by the converter warps of the GEMM kernel.
 //
+// Two GEMM kernels: mlp_gemm_tf32x3_pair_kernel (CTA pair, cta_group::2: the default) and the single-CTA
+// mlp_gemm_tf32x3_kernel it grew out of (kept for A/B runs behind ARMNET_GEMM_1CTA).
+//
 // Everything after the first Linear (its bias + BatchNorm + ReLU, the narrow hidden layers, the output Linear) is
-// one CUDA-core kernel (mlp_tail_kernel): < 3 % of the FLOPs, latency bound, so one launch instead of ~8.
+// one CUDA-core kernel (mlp_tail_kernel): < 3 % of the FLOPs, so one launch instead of ~8.
 #include <cuda.h>
 #include <stdlib.h>
 
