@@ -207,22 +207,46 @@ __device__ __forceinline__ void backward_pair(const FwdParams &P, float2 (&X)[FP
     S.y = has1 ? __ldg(P.in_tau + 2 * grow + 3) : S.x;
     const float2 invS = make_float2(__frcp_rn(S.x), __frcp_rn(S.y));
     const float2 nt = make_float2(-tau.x, -tau.y);
-    // ds = dz * z on this lane's chunk of the embedding axis, as (x, x+1) pairs
+    // ds = dz * z on this lane's chunk of the embedding axis, as (x, x+1) pairs.  16-byte loads when the rows allow it
+    // (nemb % 4 == 0): the kernel runs 8 warps per SM at 255 registers, so bytes in flight per load instruction matter.
     float2 ds[kNR][EC / 2];
+    if (EC % 4 == 0 && E % 4 == 0) {
+        const float4 *dz0 = reinterpret_cast<const float4 *>(P.in_dz + grow * E + c * EC);
+        const float4 *z0 = reinterpret_cast<const float4 *>(P.in_z + grow * E + c * EC);
+        const float4 *dz1 = reinterpret_cast<const float4 *>(P.in_dz + (grow + 1) * E + c * EC);
+        const float4 *z1 = reinterpret_cast<const float4 *>(P.in_z + (grow + 1) * E + c * EC);
 #pragma unroll
-    for (int x = 0; x < EC; ++x) {
-        const int xx = c * EC + x;
-        float d0 = 0.f, d1 = 0.f;
-        if (xx < E) {
-            d0 = __ldg(P.in_dz + grow * E + xx) * __ldg(P.in_z + grow * E + xx);
-            if (has1) d1 = __ldg(P.in_dz + (grow + 1) * E + xx) * __ldg(P.in_z + (grow + 1) * E + xx);
+        for (int x4 = 0; x4 < EC / 4; ++x4) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bz = a, a1 = a, bz1 = a;
+            if (c * EC + 4 * x4 < E) {
+                a = __ldg(dz0 + x4);
+                bz = __ldg(z0 + x4);
+                if (has1) {
+                    a1 = __ldg(dz1 + x4);
+                    bz1 = __ldg(z1 + x4);
+                }
+            }
+            ds[0][2 * x4] = make_float2(a.x * bz.x, a.y * bz.y);
+            ds[0][2 * x4 + 1] = make_float2(a.z * bz.z, a.w * bz.w);
+            ds[1][2 * x4] = make_float2(a1.x * bz1.x, a1.y * bz1.y);
+            ds[1][2 * x4 + 1] = make_float2(a1.z * bz1.z, a1.w * bz1.w);
         }
-        if (x & 1) {
-            ds[0][x / 2].y = d0;
-            ds[1][x / 2].y = d1;
-        } else {
-            ds[0][x / 2].x = d0;
-            ds[1][x / 2].x = d1;
+    } else {
+#pragma unroll
+        for (int x = 0; x < EC; ++x) {
+            const int xx = c * EC + x;
+            float d0 = 0.f, d1 = 0.f;
+            if (xx < E) {
+                d0 = __ldg(P.in_dz + grow * E + xx) * __ldg(P.in_z + grow * E + xx);
+                if (has1) d1 = __ldg(P.in_dz + (grow + 1) * E + xx) * __ldg(P.in_z + (grow + 1) * E + xx);
+            }
+            if (x & 1) {
+                ds[0][x / 2].y = d0;
+                ds[1][x / 2].y = d1;
+            } else {
+                ds[0][x / 2].x = d0;
+                ds[1][x / 2].x = d1;
+            }
         }
     }
     // mode constants for gppr = p^(2-alpha)
@@ -276,8 +300,12 @@ __device__ __forceinline__ void backward_pair(const FwdParams &P, float2 (&X)[FP
             if (valid && c == 0) {
                 const float2 w = fmul2(p, v);  // armnet.py:36
                 float *wdst = P.out_wA + (b * F + f) * (long long)R + r0;
-                wdst[0] = w.x;
-                if (has1) wdst[1] = w.y;
+                if (has1 && (R & 1) == 0) {
+                    *reinterpret_cast<float2 *>(wdst) = w;      // r0 even, R even: 8-byte aligned
+                } else {
+                    wdst[0] = w.x;
+                    if (has1) wdst[1] = w.y;
+                }
                 const float2 pv = fmul2(p, dw);  // d values (summed over the batch)
                 atomicAdd(&dV_row[f].x, pv.x);
                 if (has1) atomicAdd(&dV_row[f].y, pv.y);
@@ -302,8 +330,12 @@ __device__ __forceinline__ void backward_pair(const FwdParams &P, float2 (&X)[FP
             const float2 dg = ffma2(nq, G[f], X[f]);  // dY*gppr - q*gppr (entmax.py:76,79)
             if (valid && c == 0) {
                 float *gdst = P.out_gA + (b * F + f) * (long long)R + r0;
-                gdst[0] = dg.x;
-                if (has1) gdst[1] = dg.y;
+                if (has1 && (R & 1) == 0) {
+                    *reinterpret_cast<float2 *>(gdst) = dg;
+                } else {
+                    gdst[0] = dg.x;
+                    if (has1) gdst[1] = dg.y;
+                }
             }
             float2 e[EC / 2];
             load_e_chunk<EC>(eb + f * E_STRIDE, e);
