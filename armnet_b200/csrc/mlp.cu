@@ -120,6 +120,8 @@ __global__ void split_tf32_kernel(const float *__restrict__ w, float *__restrict
 
 struct GemmParams {
     float *out;          // [splits][MB][N][32] partial sums over each split's slice of the reduction axis
+    float *dense;        // or (splits == 1 only): the product itself, row-major [M][N] (+ bias[n] when bias != null)
+    const float *bias;
     int M, N, K;
     int MB;              // ceil(M / 32) sample blocks
     int kb_total;        // ceil(K / GK)
@@ -256,7 +258,21 @@ __global__ void __launch_bounds__(G_THREADS, 1)
             tmem_ld_32x32(tmem_acc + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 32), r);
             tmem_ld_32x32(tmem_acc + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(GN + c * 32), r2);
             tmem_ld_wait();
-            if (row < P.M) {
+            if (P.dense != nullptr) {
+                // row-major output: transpose the warp's 32 x 32 block through shared memory (the operand stages are idle
+                // now) so that every store instruction writes 128 contiguous bytes of one output row
+                float *tile = reinterpret_cast<float *>(smem) + q4 * (32 * 33);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                __syncwarp();
+                const int col = n0 + c * 32 + lane;
+                const float bv = (P.bias != nullptr && col < P.N) ? __ldg(P.bias + col) : 0.f;
+                const int row0 = m0 + q4 * 32;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr)
+                    if (row0 + rr < P.M && col < P.N) P.dense[(long long)(row0 + rr) * P.N + col] = tile[rr * 33 + lane] + bv;
+                __syncwarp();
+            } else if (row < P.M) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (n0 + c * 32 + j < P.N)
@@ -465,7 +481,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
             tmem_ld_32x32(tmem_acc + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 32), r);
             tmem_ld_32x32(tmem_acc + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(GN + c * 32), r2);
             tmem_ld_wait();
-            if (row < P.M) {
+            if (P.dense != nullptr) {
+                // row-major output: transpose the warp's 32 x 32 block through shared memory (the operand stages are idle
+                // now) so that every store instruction writes 128 contiguous bytes of one output row
+                float *tile = reinterpret_cast<float *>(smem) + q4 * (32 * 33);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                __syncwarp();
+                const int col = n0 + c * 32 + lane;
+                const float bv = (P.bias != nullptr && col < P.N) ? __ldg(P.bias + col) : 0.f;
+                const int row0 = m0 + q4 * 32;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr)
+                    if (row0 + rr < P.M && col < P.N) P.dense[(long long)(row0 + rr) * P.N + col] = tile[rr * 33 + lane] + bv;
+                __syncwarp();
+            } else if (row < P.M) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (n0 + c * 32 + j < P.N)
@@ -671,6 +701,51 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_tail_kernel(const TailParams
     }
 }
 
+// ------------------------------------------------------------------ out-of-place transpose (training GEMM operands)
+// out[c][r] = in[r][c]; 64 x 64 tiles through shared memory, 16-byte global accesses on both sides when the shapes allow.
+// The backward of the first Linear needs x^T (134 MB at config 4); the generic strided copy reaches ~1.8 TB/s.
+__global__ void __launch_bounds__(256) transpose_f32_kernel(const float *__restrict__ in, long long rows, long long cols,
+                                                            float *__restrict__ out) {
+    __shared__ float tile[64][65];
+    const long long r0 = (long long)blockIdx.y * 64, c0 = (long long)blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, each a 4-wide strip, 4 passes
+    const bool vec = (rows % 4 == 0) && (cols % 4 == 0);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int lr = ty + 16 * p;
+        const long long r = r0 + lr, c = c0 + 4 * tx;
+        if (r < rows) {
+            if (vec && c + 3 < cols) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(in + r * cols + c));
+                tile[lr][4 * tx + 0] = v.x;
+                tile[lr][4 * tx + 1] = v.y;
+                tile[lr][4 * tx + 2] = v.z;
+                tile[lr][4 * tx + 3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c + j < cols) tile[lr][4 * tx + j] = __ldg(in + r * cols + c + j);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int lc = ty + 16 * p;                    // column of the input tile = row of the output
+        const long long c = c0 + lc, r = r0 + 4 * tx;  // output row c, output columns r .. r+3
+        if (c < cols) {
+            if (vec && r + 3 < rows) {
+                *reinterpret_cast<float4 *>(out + c * rows + r) =
+                    make_float4(tile[4 * tx + 0][lc], tile[4 * tx + 1][lc], tile[4 * tx + 2][lc], tile[4 * tx + 3][lc]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (r + j < rows) out[c * rows + r + j] = tile[4 * tx + j][lc];
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -746,9 +821,9 @@ int armnet_mlp_linear_splits(int64_t B, int K, int N) {
     return (int)s;
 }
 
-int armnet_mlp_linear_tf32x3(const float *x, int64_t B, int K, const float *w_hi, const float *w_lo, int N, int splits,
-                             float *partials, void *stream) {
-    if (!x || !w_hi || !w_lo || !partials) {
+static int gemm_tf32x3_impl(const float *x, int64_t B, int K, const float *w_hi, const float *w_lo, int N, int splits,
+                           float *partials, float *dense, const float *bias, void *stream) {
+    if (!x || !w_hi || !w_lo || (!partials && !dense)) {
         set_error("armnet_mlp_linear_tf32x3: null pointer");
         return ARMNET_ERR_NULL;
     }
@@ -757,7 +832,7 @@ int armnet_mlp_linear_tf32x3(const float *x, int64_t B, int K, const float *w_hi
         return ARMNET_ERR_SHAPE;
     }
     if (K % 4 != 0 || ((uintptr_t)x & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15) ||
-        ((uintptr_t)partials & 15)) {
+        ((uintptr_t)partials & 15) || ((uintptr_t)dense & 15)) {
         set_error("armnet_mlp_linear_tf32x3: TMA needs 16-byte aligned rows (K %% 4 == 0) and base pointers");
         return ARMNET_ERR_ALIGN;
     }
@@ -769,6 +844,8 @@ int armnet_mlp_linear_tf32x3(const float *x, int64_t B, int K, const float *w_hi
     if ((rc = make_map(&ml, w_lo, N, K, w_box)) != ARMNET_OK) return rc;
     GemmParams P;
     P.out = partials;
+    P.dense = dense;
+    P.bias = bias;
     P.M = (int)B;
     P.MB = (int)((B + 31) / 32);
     P.N = N;
@@ -795,6 +872,24 @@ int armnet_mlp_linear_tf32x3(const float *x, int64_t B, int K, const float *w_hi
     ARMNET_CUDA_TRY(cudaGetLastError());
     note_launches(1);
     return ARMNET_OK;
+}
+
+int armnet_mlp_linear_tf32x3(const float *x, int64_t B, int K, const float *w_hi, const float *w_lo, int N, int splits,
+                             float *partials, void *stream) {
+    if (!partials) {
+        set_error("armnet_mlp_linear_tf32x3: null pointer");
+        return ARMNET_ERR_NULL;
+    }
+    return gemm_tf32x3_impl(x, B, K, w_hi, w_lo, N, splits, partials, nullptr, nullptr, stream);
+}
+
+int armnet_linear_tf32x3_dense(const float *x, int64_t B, int K, const float *w_hi, const float *w_lo, int N,
+                               const float *bias, float *y, void *stream) {
+    if (!y) {
+        set_error("armnet_linear_tf32x3_dense: null pointer");
+        return ARMNET_ERR_NULL;
+    }
+    return gemm_tf32x3_impl(x, B, K, w_hi, w_lo, N, 1, nullptr, y, bias, stream);
 }
 
 size_t armnet_mlp_tail_packed_floats(int H, int n_rest, int NO) {
@@ -849,3 +944,28 @@ int armnet_mlp_tail_f32(const float *partials, int splits, int64_t B, int H, int
 }
 
 }  // extern "C"
+
+extern "C" int armnet_transpose_f32(const float *in, int64_t rows, int64_t cols, float *out, void *stream) {
+    if (!in || !out) {
+        set_error("armnet_transpose_f32: null pointer");
+        return ARMNET_ERR_NULL;
+    }
+    if (rows < 0 || cols < 0) {
+        set_error("armnet_transpose_f32: bad sizes");
+        return ARMNET_ERR_SHAPE;
+    }
+    if (rows == 0 || cols == 0) return ARMNET_OK;
+    if (((uintptr_t)in & 15) || ((uintptr_t)out & 15)) {
+        set_error("armnet_transpose_f32: buffers must be 16-byte aligned");
+        return ARMNET_ERR_ALIGN;
+    }
+    dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64));
+    if (grid.y > 65535) {
+        set_error("armnet_transpose_f32: more than 65535 row tiles");
+        return ARMNET_ERR_UNSUPPORTED;
+    }
+    transpose_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, rows, cols, out);
+    ARMNET_CUDA_TRY(cudaGetLastError());
+    note_launches(1);
+    return ARMNET_OK;
+}

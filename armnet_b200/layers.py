@@ -62,7 +62,8 @@ class MLP(nn.Module):
         mods.append(nn.Linear(nhid, noutput))
         self.mlp = nn.Sequential(*mods)
         self.nhid = nhid
-        self.tensor_core = True     # host-side knob (not in state_dict)
+        self.tensor_core = True     # host-side knobs (not in state_dict)
+        self.train_tensor_core = True   # training: first Linear's three GEMMs on tcgen05 (large batches only)
         self._cache_key = None
         self._cache = None
 
@@ -88,4 +89,12 @@ class MLP(nn.Module):
             w_hi, w_lo, packed = self._prepared()
             partials = ops.mlp_first_linear(x, w_hi, w_lo)
             return ops.mlp_tail(partials, packed, self.nlayers - 1, self.noutput, x.shape[0])
+        if (self.tensor_core and self.train_tensor_core and torch.is_grad_enabled() and x.is_cuda and x.dim() == 2
+                and x.dtype == torch.float32 and self.nlayers >= 1 and self.ninput % 4 == 0 and self.nhid % 4 == 0
+                and x.shape[0] % 4 == 0 and x.shape[0] >= 512 and self.ninput >= 1024):
+            # training at scale: the wide first Linear (forward, dX, dW) on the tensor cores, the rest stock torch
+            h = ops.linear_tf32x3(x, self.mlp[0].weight, self.mlp[0].bias)
+            for mod in list(self.mlp)[1:]:
+                h = mod(h)
+            return h
         return self.mlp(x)

@@ -10,7 +10,7 @@ import torch
 from . import _capi
 from ._capi import SOLVER_AUTO, SOLVER_BISECT, check, lib
 
-__all__ = ['linear_gather', 'batch_norm_train', 'clamp_adam', 'partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
+__all__ = ['transpose2d', 'linear_tf32x3', 'linear_dense', 'linear_gather', 'batch_norm_train', 'clamp_adam', 'partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
            'SOLVER_AUTO', 'SOLVER_BISECT', 'last_launch_count']
 
 
@@ -333,6 +333,72 @@ def mlp_tail(partials, packed, n_rest, noutput, B):
     check(lib.armnet_mlp_tail_f32(partials.data_ptr(), S, B, H, n_rest, noutput, packed.data_ptr(), y.data_ptr(),
                                   _stream()), 'armnet_mlp_tail_f32')
     return y
+
+
+def linear_dense(x, w_hi, w_lo, bias=None):
+    """armnet_linear_tf32x3_dense: y [B,N] = x [B,K] . w^T (+ bias) on tcgen05 (3xTF32), row-major output."""
+    _need_cuda(x, w_hi, w_lo)
+    x = _f32c(x, 'x')
+    B, K = x.shape
+    N = w_hi.shape[0]
+    assert w_hi.shape == (N, K) and w_lo.shape == (N, K) and w_hi.is_contiguous() and w_lo.is_contiguous()
+    y = torch.empty(B, N, dtype=torch.float32, device=x.device)
+    check(lib.armnet_linear_tf32x3_dense(x.data_ptr(), B, K, w_hi.data_ptr(), w_lo.data_ptr(), N,
+                                         bias.data_ptr() if bias is not None else None, y.data_ptr(), _stream()),
+          'armnet_linear_tf32x3_dense')
+    return y
+
+
+def transpose2d(x):
+    """armnet_transpose_f32: contiguous [cols, rows] copy of a contiguous fp32 [rows, cols] CUDA tensor."""
+    _need_cuda(x)
+    x = _f32c(x, 'x')
+    rows, cols = x.shape
+    out = torch.empty(cols, rows, dtype=torch.float32, device=x.device)
+    check(lib.armnet_transpose_f32(x.data_ptr(), rows, cols, out.data_ptr(), _stream()), 'armnet_transpose_f32')
+    return out
+
+
+class _LinearTF32x3Fn(torch.autograd.Function):
+    """F.linear(x, W, b) for training with all three GEMMs on the tcgen05 3xTF32 kernel (fp32 parity):
+         y  [B,N] = x . W^T + b        split-K partial sums (K = ninput is long), summed here
+         dx [B,K] = dy . W             dense output (reduction over N = nhid is short)
+         dW [N,K] = dy^T . x           computed as (x^T . dy)^T: the big operand is the one converted in-kernel
+    Needs K % 4 == 0, N % 4 == 0, B % 4 == 0 (TMA row pitches)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        x = _f32c(x, 'x')
+        hi, lo = mlp_split_weight(W)
+        y = partials_to_dense(mlp_first_linear(x, hi, lo), x.shape[0])
+        if b is not None:
+            y = y + b
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = _f32c(dy, 'dy')
+        B = x.shape[0]
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            wt_hi, wt_lo = mlp_split_weight(transpose2d(W.detach()))              # [K, N]
+            dx = linear_dense(dy, wt_hi, wt_lo)
+        if ctx.needs_input_grad[1]:
+            dyt_hi, dyt_lo = mlp_split_weight(transpose2d(dy))                    # [N, B]
+            xt = transpose2d(x)                                                   # [K, B]
+            dWt = partials_to_dense(mlp_first_linear(xt, dyt_hi, dyt_lo), xt.shape[0])   # [K, N]
+            dW = dWt.t()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dW, db
+
+
+def linear_tf32x3(x, weight, bias=None):
+    """Differentiable F.linear on the tensor cores with fp32 parity (see _LinearTF32x3Fn)."""
+    return _LinearTF32x3Fn.apply(x, weight, bias)
 
 
 def clamp_adam(param, grad, exp_avg, exp_avg_sq, grad_scale, clamp, lr, beta1, beta2, eps, step):

@@ -159,6 +159,12 @@ int armnet_mlp_split_weight_f32(const float *w, int64_t n, float *w_hi, float *w
 int armnet_mlp_linear_splits(int64_t B, int K, int N);
 int armnet_mlp_linear_tf32x3(const float *x, int64_t B, int K, const float *w_hi, const float *w_lo, int N, int splits,
                              float *partials, void *stream);
+/* The same GEMM with the product written directly, row-major: y [B,N] = x . w^T (+ bias[n] when bias != NULL), the whole
+ * reduction axis in one accumulation chain (meant for short K; training uses it for dX = dY . W). */
+int armnet_linear_tf32x3_dense(const float *x, int64_t B, int K, const float *w_hi, const float *w_lo, int N,
+                               const float *bias, float *y, void *stream);
+/* out [cols, rows] = in [rows, cols]^T (tiled through shared memory); operands of the training GEMMs (x^T, W^T, dY^T). */
+int armnet_transpose_f32(const float *in, int64_t rows, int64_t cols, float *out, void *stream);
 size_t armnet_mlp_tail_packed_floats(int H, int n_rest, int NO);
 int armnet_mlp_tail_f32(const float *partials, int splits, int64_t B, int H, int n_rest, int NO, const float *packed,
                         float *y, void *stream);

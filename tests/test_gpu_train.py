@@ -174,3 +174,40 @@ def test_training_trajectory_matches_reference(case, optimizer):
         errs[k[6:]] = (a - b).abs().max().item() / max(b.abs().max().item(), 1e-6)
     print({k: float(f'{v:.1e}') for k, v in sorted(errs.items(), key=lambda kv: -kv[1])[:6]})
     assert max(errs.values()) <= 2e-3, errs    # Adam divides by sqrt(v): tiny gradient differences are amplified
+
+
+@pytest.mark.parametrize('B,K,N', [(4096, 8192, 256), (512, 1024, 64), (1028, 1500, 36)])
+def test_linear_tf32x3_forward_backward_match_fp64(B, K, N):
+    """The training-mode first Linear on tcgen05 (ops.linear_tf32x3: y, dx, dW, db) against an fp64 evaluation; the stock
+    fp32 cuBLAS path is measured next to it."""
+    from armnet_b200 import ops
+    torch.manual_seed(B + N)
+    x = torch.randn(B, K, device=dev())
+    W = (torch.randn(N, K, device=dev()) * K ** -0.5)
+    b = torch.randn(N, device=dev()) * 0.1
+    gy = torch.randn(B, N, device=dev())
+
+    def run(fn, dtype):
+        xx, ww, bb = (t.detach().to(dtype).requires_grad_(True) for t in (x, W, b))
+        y = fn(xx, ww, bb)
+        y.backward(gy.to(dtype))
+        return y.detach(), xx.grad, ww.grad, bb.grad
+
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = run(torch.nn.functional.linear, torch.float64)
+    stock = run(torch.nn.functional.linear, torch.float32)
+    torch.backends.cuda.matmul.allow_tf32 = old
+    ours = run(ops.linear_tf32x3, torch.float32)
+    for name, o, s_, r in zip(('y', 'dx', 'dW', 'db'), ours, stock, ref):
+        eo = ((o.double() - r).abs().max() / r.abs().max()).item()
+        es = ((s_.double() - r).abs().max() / r.abs().max()).item()
+        print(f'B={B} K={K} N={N} {name}: tcgen05 3xTF32 err {eo:.2e}, cuBLAS fp32 err {es:.2e}')
+        assert eo <= 1e-5, name
+
+
+@pytest.mark.parametrize('rows,cols', [(4096, 8192), (257, 130), (64, 64), (1, 7), (1000, 36)])
+def test_transpose2d(rows, cols):
+    from armnet_b200 import ops
+    x = torch.randn(rows, cols, device=dev())
+    assert torch.equal(ops.transpose2d(x), x.t().contiguous())
