@@ -43,6 +43,9 @@ SIGNATURES = {
     'armnet_libsvm_count_lines': (_I, [C.c_char_p, C.POINTER(_L)]),
     'armnet_libsvm_parse': (_I, [C.c_char_p, _I, _L, _P, _P, _P, C.POINTER(_L), C.POINTER(_L)]),
     'armnet_clamp_adam_f32': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _L, _P]),
+    'armnet_fused_prepare_f32': (_I, [_P, _P, _P, _I, _F, _I, _I, _I, _I, _I, _P, _P]),
+    'armnet_fused_fwd_prepared_f32': (_I, [_P, _I, _P, _P, _L, _L, _F, _I, _I, _L, _I, _I, _I, _I, _I,
+                                           _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'armnet_fused_fwd_f32': (_I, [_P, _I, _P, _P, _L, _L, _P, _P, _P, _I, _F, _I, _I, _L, _I, _I, _I, _I, _I,
                                   _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }

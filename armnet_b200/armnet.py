@@ -82,6 +82,9 @@ class ARMNetModel(nn.Module):
         self.fuse_bn = True          # eval mode: apply arm_bn in the kernel epilogue
         self.fused_backward = True   # training: fused backward kernel (else unfused autograd stages)
         self.cuda_bn = True          # training: arm_bn batch statistics by csrc/bn.cu (else nn.BatchNorm1d / cuDNN)
+        self.cache_attention = True  # no-grad mode: pre-contract the attention parameters once per weight version
+        self._attn_key = None
+        self._attn_ws = None
         self._shadow = _PaddedTable()
         self._err_flag = None
         self._bn_key = None
@@ -112,10 +115,20 @@ class ARMNetModel(nn.Module):
         W, Q, Vv = self._attn_weights()
         if self.validate_ids and (self._err_flag is None or self._err_flag.device != table.device):
             self._err_flag = ops.new_error_flag(table.device)
+        prepared = None
+        if self.cache_attention and not torch.is_grad_enabled():
+            # serving: the attention parameters are pre-contracted once per weight version, not once per batch
+            key = (W.data_ptr(), W._version, Q.data_ptr(), Q._version, Vv.data_ptr(), Vv._version, self.alpha,
+                   x['id'].shape[1])
+            if self._attn_key != key:
+                self._attn_ws = ops.fused_prepare(W.detach(), Q.detach(), Vv.detach(), self.alpha, x['id'].shape[1],
+                                                  one_head=self.one_head)
+                self._attn_key = key
+            prepared = self._attn_ws
         z, extra = ops.fused_forward(x['id'], x['value'], tab, W.detach(), Q.detach(), Vv.detach(), self.alpha,
                                      one_head=self.one_head, solver=self.solver, ld=ld, nemb=table.shape[1],
                                      err_flag=self._err_flag if self.validate_ids else None,
-                                     post=self._folded_bn() if fold_bn else None, **want)
+                                     post=self._folded_bn() if fold_bn else None, prepared=prepared, **want)
         if self.validate_ids:
             ops.raise_if_bad_ids(self._err_flag)
         return (z, extra) if want else z

@@ -59,6 +59,9 @@ class ARMNetModel(_MultiHead):
         self.fuse_bn = True
         self.fused_backward = True
         self.cuda_bn = True
+        self.cache_attention = True
+        self._attn_key = None
+        self._attn_ws = None
         self._shadow = _PaddedTable()
         self._err_flag = None
         self._bn_key = None

@@ -115,10 +115,13 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
                         int F, int E, int D, int K, int O, int clamp, float clamp_lo, float clamp_hi, int clamp_inplace,
                         const float *post_mean, const float *post_scale, const float *post_shift, float *out_z,
                         float *out_tau, float *out_p, float *out_g, float *out_s, void *workspace, int *err_flag,
-                        void *stream) {
+                        void *stream, int mode = 0) {
+    // mode 0: pre-contract the attention parameters into `workspace`, then run; 1: pre-contract only; 2: run only
+    // (`workspace` was filled by an earlier mode-1 call with the same parameters, alpha and shape)
     note_launches(0);
     if (B == 0) return ARMNET_OK;  // empty batch: nothing to read or write (tensors may have null data pointers)
-    if (!ids || !values || !table || !bilinear_w || !query || !att_values || !workspace || (!bwd && !out_z) ||
+    if (!ids || !values || !table || (mode != 2 && (!bilinear_w || !query || !att_values)) || !workspace ||
+        (!bwd && !out_z) ||
         (bwd && (!bwd->z || !bwd->dz || !bwd->tau || !bwd->wA || !bwd->gA || !bwd->dV || !bwd->dM))) {
         set_error("%s: null pointer", who);
         return ARMNET_ERR_NULL;
@@ -275,18 +278,22 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
     const SmemLayout L(I->FP, E_lanes, E_stride, ES, P, bwd != nullptr);
 
     cudaStream_t st = (cudaStream_t)stream;
-    {
+    if (mode != 2) {
         const int total = R2 * (mstr + vstr) * 2;
         int blocks = (total + 255) / 256;
         if (blocks > di.sm_count * 4) blocks = di.sm_count * 4;
         attn_prepare_kernel<<<blocks, 256, 0, st>>>(bilinear_w, query, att_values, w_is_linear_layout, F, E, D, O, R, R2,
                                                      E_lanes, mstr, vstr, scale, P.ep.am1, Mg2, Vg2);
         ARMNET_CUDA_TRY(cudaGetLastError());
+        if (mode == 1) {
+            note_launches(1);
+            return ARMNET_OK;
+        }
     }
     ARMNET_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
     void *args[] = {(void *)&P};
     ARMNET_CUDA_TRY(cudaLaunchKernel(kernel, dim3(grid), dim3(P.NW * 32), args, (size_t)L.total, st));
-    note_launches(2);
+    note_launches(mode == 2 ? 1 : 2);
     return ARMNET_OK;
 }
 
@@ -303,6 +310,28 @@ extern "C" int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values,
                                 w_is_linear_layout, alpha, solver, n_iter, B, F, E, D, K, O, clamp, clamp_lo, clamp_hi,
                                 clamp_inplace, post_mean, post_scale, post_shift, out_z, out_tau, out_p, out_g, out_s,
                                 workspace, err_flag, stream);
+}
+
+extern "C" int armnet_fused_prepare_f32(const float *bilinear_w, const float *query, const float *att_values,
+                                        int w_is_linear_layout, float alpha, int F, int E, int D, int K, int O,
+                                        void *workspace, void *stream) {
+    // the batch arguments are not touched in mode 1; `workspace` stands in for them to pass the pointer checks
+    float *w = static_cast<float *>(workspace);
+    return armnet::launch_fused("fused_prepare", nullptr, workspace, 1, w, w, 1, E, bilinear_w, query, att_values,
+                                w_is_linear_layout, alpha, ARMNET_SOLVER_AUTO, 50, 1, F, E, D, K, O, 0, 0.f, 0.f, 0, nullptr,
+                                nullptr, nullptr, w, nullptr, nullptr, nullptr, nullptr, workspace, nullptr, stream, 1);
+}
+
+extern "C" int armnet_fused_fwd_prepared_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V,
+                                             int64_t ld, float alpha, int solver, int n_iter, int64_t B, int F, int E, int D,
+                                             int K, int O, int clamp, float clamp_lo, float clamp_hi, int clamp_inplace,
+                                             const float *post_mean, const float *post_scale, const float *post_shift,
+                                             float *out_z, float *out_tau, float *out_p, float *out_g, float *out_s,
+                                             const void *workspace, int *err_flag, void *stream) {
+    return armnet::launch_fused("fused_fwd_prepared", nullptr, ids, ids_i32, values, table, V, ld, nullptr, nullptr, nullptr,
+                                0, alpha, solver, n_iter, B, F, E, D, K, O, clamp, clamp_lo, clamp_hi,
+                                clamp_inplace, post_mean, post_scale, post_shift, out_z, out_tau, out_p, out_g, out_s,
+                                const_cast<void *>(workspace), err_flag, stream, 2);
 }
 
 extern "C" int armnet_fused_bwd_supported(int F, int E) {

@@ -10,7 +10,7 @@ import torch
 from . import _capi
 from ._capi import SOLVER_AUTO, SOLVER_BISECT, check, lib
 
-__all__ = ['transpose2d', 'linear_tf32x3', 'linear_dense', 'linear_gather', 'batch_norm_train', 'clamp_adam', 'partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
+__all__ = ['fused_prepare', 'transpose2d', 'linear_tf32x3', 'linear_dense', 'linear_gather', 'batch_norm_train', 'clamp_adam', 'partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
            'SOLVER_AUTO', 'SOLVER_BISECT', 'last_launch_count']
 
 
@@ -133,7 +133,7 @@ def entmax(x, alpha=1.5, dim=-1, n_iter=50, solver=SOLVER_AUTO):
 def fused_forward(ids, values, table, bilinear_w, query, att_values, alpha, one_head=False, n_iter=50,
                   solver=SOLVER_AUTO, clamp: Optional[Tuple[float, float]] = (0.001, 1.0), clamp_inplace=True,
                   ld: Optional[int] = None, nemb: Optional[int] = None, want_tau=False, want_p=False,
-                  want_g=False, want_s=False, err_flag=None, post=None):
+                  want_g=False, want_s=False, err_flag=None, post=None, prepared=None):
     """The fused hot path (armnet.py:82-87 / armnet_1h.py:81-86): returns z [B, K*O, E] and a dict of the optional
     outputs ('tau' [B,K*O,2], 'p' [B,K*O,F], 'g' [B,K*O,F], 's' [B,K*O,E]).
     post=(mean, scale, shift), each [K*O]: eval-mode arm_bn epilogue z <- (z - mean) * scale + shift (armnet.py:89)."""
@@ -159,7 +159,9 @@ def fused_forward(ids, values, table, bilinear_w, query, att_values, alpha, one_
     ws_bytes = lib.armnet_fused_workspace_bytes(F, E, K, O)
     if ws_bytes == 0:
         raise _capi.ArmnetError(f'armnet_fused_fwd_f32: unsupported shape F={F} E={E} (F <= 64, E <= 128)')
-    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+    if prepared is not None:
+        assert prepared.numel() * 4 == ws_bytes and prepared.is_cuda
+    ws = prepared if prepared is not None else torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
     z = torch.empty(B, R, E, dtype=torch.float32, device=dev)
     extra = {}
     if want_tau:
@@ -180,6 +182,15 @@ def fused_forward(ids, values, table, bilinear_w, query, att_values, alpha, one_
     def ptr(k):
         return extra[k].data_ptr() if k in extra else None
 
+    if prepared is not None:     # serving: the pre-contracted attention parameters are reused (read-only) across batches
+        rc = lib.armnet_fused_fwd_prepared_f32(
+            ids_c.data_ptr(), _ids_arg(ids_c), values.data_ptr(), table.data_ptr(), V, ld, float(alpha), int(solver),
+            int(n_iter), B, F, E, D, K, O, int(clamp is not None), lo, hi, int(clamp_inplace),
+            pm.data_ptr() if post is not None else None, ps.data_ptr() if post is not None else None,
+            pb.data_ptr() if post is not None else None, z.data_ptr(), ptr('tau'), ptr('p'), ptr('g'), ptr('s'),
+            ws.data_ptr(), err_flag.data_ptr() if err_flag is not None else None, _stream())
+        check(rc, 'armnet_fused_fwd_prepared_f32')
+        return z, extra
     rc = lib.armnet_fused_fwd_f32(
         ids_c.data_ptr(), _ids_arg(ids_c), values.data_ptr(), table.data_ptr(), V, ld, W.data_ptr(), Q.data_ptr(),
         Vv.data_ptr(), int(one_head), float(alpha), int(solver), int(n_iter), B, F, E, D, K, O,
@@ -189,6 +200,25 @@ def fused_forward(ids, values, table, bilinear_w, query, att_values, alpha, one_
         ptr('s'), ws.data_ptr(), err_flag.data_ptr() if err_flag is not None else None, _stream())
     check(rc, 'armnet_fused_fwd_f32')
     return z, extra
+
+
+def fused_prepare(bilinear_w, query, att_values, alpha, F, one_head=False):
+    """armnet_fused_prepare_f32: the pre-contracted attention parameters for fused_forward(..., prepared=ws)."""
+    _need_cuda(bilinear_w, query, att_values)
+    W, Q, Vv = _f32c(bilinear_w, 'bilinear_w'), _f32c(query, 'query'), _f32c(att_values, 'values')
+    if one_head:
+        D, E = W.shape
+        K, O = 1, Q.shape[0]
+    else:
+        K, E, D = W.shape
+        O = Q.shape[1]
+    ws_bytes = lib.armnet_fused_workspace_bytes(F, E, K, O)
+    if ws_bytes == 0:
+        raise _capi.ArmnetError(f'armnet_fused_prepare_f32: unsupported shape F={F} E={E} (F <= 64, E <= 128)')
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=W.device)
+    check(lib.armnet_fused_prepare_f32(W.data_ptr(), Q.data_ptr(), Vv.data_ptr(), int(one_head), float(alpha), F, E, D, K, O,
+                                       ws.data_ptr(), _stream()), 'armnet_fused_prepare_f32')
+    return ws
 
 
 def fused_bwd_supported(F, E):

@@ -116,6 +116,23 @@ int armnet_fused_fwd_f32(const void *ids, int ids_i32, float *values, const floa
                          float *out_s, void *workspace, int *err_flag, void *stream);
 
 /*
+ * The same forward split in two for serving, where the attention parameters do not change between batches:
+ *   armnet_fused_prepare_f32        pre-contracts (bilinear_w, query, att_values, alpha) into `workspace` (one small launch);
+ *   armnet_fused_fwd_prepared_f32   runs the fused kernel on a batch with such a workspace, which it only READS -- it can be
+ *                                   shared by concurrent streams.  Same arguments and semantics as armnet_fused_fwd_f32
+ *                                   otherwise; alpha, F, E, D, K, O must be the ones the workspace was prepared with.
+ */
+int armnet_fused_prepare_f32(const float *bilinear_w, const float *query, const float *att_values,
+                             int w_is_linear_layout, float alpha, int F, int E, int D, int K, int O, void *workspace,
+                             void *stream);
+int armnet_fused_fwd_prepared_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V, int64_t ld,
+                                  float alpha, int solver, int n_iter, int64_t B, int F, int E, int D, int K, int O,
+                                  int clamp, float clamp_lo, float clamp_hi, int clamp_inplace, const float *post_mean,
+                                  const float *post_scale, const float *post_shift, float *out_z, float *out_tau,
+                                  float *out_p, float *out_g, float *out_s, const void *workspace, int *err_flag,
+                                  void *stream);
+
+/*
  * Backward of the fused hot path w.r.t. its parameters (what autograd derives for models/armnet.py:82-87 with
  * EntmaxBisectFunction.backward, utils/entmax.py:71-80).  Per (sample, neuron) row it rebuilds the gates from the
  * (tau, sum) pairs the forward saved in out_tau and emits

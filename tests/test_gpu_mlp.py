@@ -145,3 +145,28 @@ def test_full_size_eval_forward_matches_oracle():
     print(f'full-size eval forward: max |y - oracle| / scale = {err:.2e}')
     assert err <= 2e-5
     assert torch.equal(y2, y)                                             # same kernels, same results, graph or not
+
+
+def test_prepared_attention_workspace_equals_per_call_preparation():
+    """armnet_fused_prepare_f32 + armnet_fused_fwd_prepared_f32 == armnet_fused_fwd_f32, bit for bit, and the module's
+    cache follows parameter updates."""
+    import armnet_b200 as ab
+    from armnet_b200 import ops
+    torch.manual_seed(1)
+    F, V, B = 39, 3000, 200
+    m = ab.ARMNetModel(F, V, 10, 4, 1.7, 32, 2, 32, 0.0, False, 2, 32).to(dev()).eval()
+    ids = torch.randint(0, V, (B, F), device=dev())
+    vals = torch.rand(B, F, device=dev())
+    W, Q, Vv = (t.detach() for t in m._attn_weights())
+    tab = m.embedding.embedding.weight.detach()
+    z0, _ = ops.fused_forward(ids, vals.clone(), tab, W, Q, Vv, 1.7)
+    ws = ops.fused_prepare(W, Q, Vv, 1.7, F)
+    z1, _ = ops.fused_forward(ids, vals.clone(), tab, W, Q, Vv, 1.7, prepared=ws)
+    assert torch.equal(z0, z1) and ops.last_launch_count() == 1
+    with torch.no_grad():
+        y0 = m({'id': ids, 'value': vals.clone()})
+        m.attn_layer.query.mul_(1.5)                       # in-place update -> version bump -> cache rebuilt
+        y1 = m({'id': ids, 'value': vals.clone()})
+        m.cache_attention = False
+        y2 = m({'id': ids, 'value': vals.clone()})
+    assert not torch.equal(y0, y1) and torch.equal(y1, y2)
