@@ -47,13 +47,13 @@ WORKLOADS = {
                mlp_nlayer=2, mlp_nhid=256),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of armnet_fwd_kernel from the committed `ncu --set full`
-# capture (profiles/r1_v5_summary.md, r1_v5_fwd_ncu.txt): 21.82 MB read + 25.13 MB written. Below the algorithmic 92.2 MB because part
+# capture (profiles/r1_v6_fwd_ncu.txt): 21.82 MB read + 26.51 MB written. Below the algorithmic 92.2 MB because part
 # of the 84 MB output is still dirty in the 126 MB L2 when the kernel ends; no re-reads.
-NCU_TRAFFIC_BYTES = {'c2a': 46956288}
+NCU_TRAFFIC_BYTES = {'c2a': 48326912}
 # FP32-pipe lane-cycles per (sample, neuron) row of armnet_fwd_kernel<39,1,10,1> from the same capture's executed-opcode
-# histogram (profiles/r1_v5_fwd_ncu.txt): FFMA2 409.5, FADD2 98, FMUL2 64 (2 pipe cycles each) + FADD 53, FFMA 44, FMUL 16.5.
+# histogram (profiles/r1_v6_fwd_ncu.txt): FFMA2 409.5, FADD2 98, FMUL2 64 (2 pipe cycles each) + FADD 43 (+ a few FFMA / FMUL).
 # Used for the honest second ceiling: the path is FP32-issue bound, not HBM bound.
-NCU_FP32_PIPE_CYCLES_PER_ROW = {'c2a': 2 * (409.5 + 98.0 + 64.0) + 53.0 + 44.0 + 16.5}
+NCU_FP32_PIPE_CYCLES_PER_ROW = {'c2a': 2 * (409.5 + 98.0 + 64.0) + 43.0 + 8.0}
 METRIC = 'CTR samples/sec (bsz=4096, Criteo-shape) at 1/2/4/8 B200; HBM GB/s vs roofline'
 
 
@@ -363,7 +363,7 @@ def main():
         need = rows_per_s / 32.0 * NCU_FP32_PIPE_CYCLES_PER_ROW[args.workload]   # one warp instruction serves 32 row-threads
         have = 148 * 4 * clocks['sm_mhz'] * 1e6
         fp32_pipe = {'frac': need / have, 'what': 'FMA-pipe busy fraction implied by the measured rate and the ncu '
-                     'opcode histogram (ncu direct: sm__pipe_fma_cycles_active 52.7 %)'}
+                     'opcode histogram (ncu direct: sm__pipe_fma_cycles_active 51.7 %)'}
     out = {
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': n, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
