@@ -21,6 +21,10 @@ same kernels ARMNetModel.forward launches.
 
 Unlike ARMNetModel.forward, the caller's host `value` tensor is NOT clamped in place (the clamp of armnet.py:82 is
 applied to the device copy).
+
+The captured graphs hold pointers to parameter-derived caches (padded table, pre-contracted attention matrix, split MLP
+weights).  submit() compares the parameters' version counters with the ones seen at capture time and re-captures when
+they changed (in-place updates such as optimizer steps or load_state_dict bump the counters).
 """
 import torch
 
@@ -59,14 +63,19 @@ class BatchScorer:
         for i, s in enumerate(self.slots):
             s.stream = self.compute_streams[i % len(self.compute_streams)]
         self.n_submitted = 0
+        self._tensors = list(model.parameters()) + [b for b in model.buffers() if b.dtype.is_floating_point]
         self._prepare()
 
     def _forward(self, slot):
         with torch.no_grad():
             return self.model({'id': slot.ids, 'value': slot.vals}).reshape(-1)
 
+    def _version_key(self):
+        return tuple(t._version for t in self._tensors)
+
     def _prepare(self):
         """Warm every lazily built cache (padded table, folded BatchNorm, split weights), then capture one graph per slot."""
+        self._key = self._version_key()
         for s in self.slots:
             cs = s.stream
             cs.wait_stream(torch.cuda.current_stream(self.dev))
@@ -88,6 +97,11 @@ class BatchScorer:
         outstanding: result(t) must have been called before submit() reuses its slot."""
         if tuple(ids_host.shape) != (self.B, self.F) or tuple(values_host.shape) != (self.B, self.F):
             raise ValueError(f'BatchScorer was built for batches of shape {(self.B, self.F)}')
+        if self.use_graph and self._version_key() != self._key:     # parameters changed since capture: rebuild
+            torch.cuda.synchronize(self.dev)
+            for sl in self.slots:
+                sl.graph = None
+            self._prepare()
         t = self.n_submitted
         s = self.slots[t % self.depth]
         if s.used:

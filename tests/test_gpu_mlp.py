@@ -111,6 +111,13 @@ def test_batch_scorer_matches_module_forward(use_graph, depth, streams):
     assert torch.equal(batches[0][1], batches[0][1].clone())     # host values are not clamped in place
     with pytest.raises(ValueError):
         scorer.submit(batches[0][0][:10], batches[0][1][:10])
+    # parameters updated in place after capture: the scorer re-captures and follows them
+    with torch.no_grad():
+        model.attn_layer.values.mul_(1.3)
+        model.mlp.mlp[0].weight.mul_(0.9)
+        want2 = model({'id': batches[1][0].to(dev()), 'value': batches[1][1].clone().to(dev())}).cpu()
+    got2 = scorer.result(scorer.submit(*batches[1])).clone()
+    assert torch.equal(got2, want2) and not torch.equal(got2, want[1])
 
 
 def test_full_size_eval_forward_matches_oracle():

@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 python -m pytest tests/test_gpu_mlp.py -q -s -x 2>&1 | tail -30 | tee gpurun_out/pytest_mlp.log
-timeout 120 python tools/bench_mlp.py 2>&1 | tail -12 | tee gpurun_out/bench_mlp.log
-ARMNET_GEMM_1CTA=1 timeout 120 python tools/bench_mlp.py 2>&1 | tail -12 | head -6
+timeout 200 python -m pytest tests/test_gpu_mlp.py -q -x 2>&1 | tail -4 | tee gpurun_out/pytest_mlp.log
+timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n1_r1k.json; python tools/show_bench.py gpurun_out/bench_n1_r1k.json 2>/dev/null | head -1
