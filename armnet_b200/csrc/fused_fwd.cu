@@ -4,9 +4,13 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "fused_fwd.cuh"
+#include "fused_fwd_mma.cuh"
 
 namespace armnet {
+
+// Tensor-core instances (fused_fwd_mma.cu).
+extern const MmaInstance kMmaInstances[];
+extern const int kNumMmaInstances;
 
 // Tables of compiled shapes, one per translation unit so they build in parallel.
 extern const FwdInstance kFwdInstancesA[];
@@ -88,6 +92,20 @@ __global__ void attn_prepare_kernel(const float *__restrict__ W, const float *__
 
 static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
+// The tensor-core kernel for this shape, or null (see the requirements in fused_fwd_mma.cuh).  `I` is the
+// armnet_fwd_kernel instance of the shape: the pair tables in the workspace are laid out for it.
+static const MmaInstance *select_mma_instance(const FwdInstance *I, int F, int E, int R, int mode) {
+    // opt-in: measured on B200 at C2a it is 14 % slower than armnet_fwd_kernel (24.1 M vs 27.9 M samples/s): what the MMAs
+    // save in FFMA2s comes back as operand splits, quad shuffles and register moves (profiles/r1_v7_mma_experiment.md)
+    const char *on = getenv("ARMNET_MMA");
+    if (!on || on[0] != '1' || I->ES != 1 || R % 64 != 0 || mode == POW_BISECT) return nullptr;
+    for (int i = 0; i < kNumMmaInstances; ++i) {
+        const MmaInstance &M = kMmaInstances[i];
+        if (F > 8 * (M.NT - 1) && F <= 8 * M.NT && E == 8 * M.EK + M.ER && round_up(I->EC, 4) == M.E_STRIDE) return &M;
+    }
+    return nullptr;
+}
+
 }  // namespace armnet
 
 extern "C" size_t armnet_fused_workspace_bytes(int F, int E, int K, int O) {
@@ -148,11 +166,20 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
         return ARMNET_ERR_UNSUPPORTED;
     }
     const void *kernel = bwd ? I->kernel_bwd : I->kernel;
-    const int max_warps = bwd ? kBwdWarps : kMaxWarps;
+    int max_warps = bwd ? kBwdWarps : kMaxWarps;
     FwdParams P;
     memset(&P, 0, sizeof(P));
     int rc = make_entmax_params(alpha, F, solver, n_iter, &P.ep);
     if (rc != ARMNET_OK) return rc;
+    if (!bwd) {
+        if (const MmaInstance *M = select_mma_instance(I, F, E, K * O, P.ep.mode)) {
+            const char *sp = getenv("ARMNET_MMA_SPLIT");
+            kernel = (sp && sp[0] == 'r') ? M->kernel_rna : M->kernel;
+            max_warps = kMmaWarps;
+        }
+    }
+    P.tabFP = I->FP;
+    P.tabEL = I->EC * I->ES;
     DeviceInfo di;
     rc = get_device_info(&di);
     if (rc != ARMNET_OK) return rc;
@@ -337,6 +364,15 @@ extern "C" int armnet_fused_fwd_prepared_f32(const void *ids, int ids_i32, float
 extern "C" int armnet_fused_bwd_supported(int F, int E) {
     const armnet::FwdInstance *I = armnet::select_instance(F, E);
     return (I && I->kernel_bwd) ? 1 : 0;
+}
+
+extern "C" int armnet_fused_fwd_kernel_kind(int F, int E, int K, int O, float alpha, int solver) {
+    using namespace armnet;
+    if (F <= 0 || E <= 0 || K <= 0 || O <= 0) return 0;
+    const FwdInstance *I = select_instance(F, E);
+    EntmaxParams ep;
+    if (!I || make_entmax_params(alpha, F, solver, 50, &ep) != ARMNET_OK) return 0;
+    return select_mma_instance(I, F, E, K * O, ep.mode) ? 2 : 1;
 }
 
 extern "C" int armnet_fused_bwd_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V,

@@ -80,6 +80,7 @@ struct FwdParams {
     int row_bytes;
     int tma_store;   // 1: z staged in shared memory and written with cp.async.bulk
     int lockstep;    // 1: static unit assignment with a CTA barrier per round; 0: dynamic unit counter
+    int tabFP, tabEL;  // armnet_fwd_mma_kernel: field / embedding-lane counts the pair tables in `workspace` were laid out for
 };
 
 __host__ __device__ constexpr int round_up_c(int x, int a) { return (x + a - 1) / a * a; }

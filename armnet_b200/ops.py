@@ -225,6 +225,11 @@ def fused_bwd_supported(F, E):
     return bool(lib.armnet_fused_bwd_supported(int(F), int(E)))
 
 
+def fused_fwd_kernel_kind(F, E, K, O, alpha, solver=0):
+    """0: no instance, 1: armnet_fwd_kernel (FP32 pipe), 2: armnet_fwd_mma_kernel (TF32 tensor-core products)."""
+    return int(lib.armnet_fused_fwd_kernel_kind(int(F), int(E), int(K), int(O), float(alpha), int(solver)))
+
+
 def fused_backward(ids, values, table, bilinear_w, query, att_values, alpha, z, dz, tau, one_head=False,
                    ld: Optional[int] = None, nemb: Optional[int] = None):
     """armnet_fused_bwd_f32: returns (w [B,F,R], dg [B,F,R], dvalues [R,F], dm [R,E]); see include/armnet_b200.h."""

@@ -49,7 +49,7 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of armnet_fwd_kernel from the committed `ncu --set full`
 # capture (profiles/r1_v6_fwd_ncu.txt): 21.82 MB read + 26.51 MB written. Below the algorithmic 92.2 MB because part
 # of the 84 MB output is still dirty in the 126 MB L2 when the kernel ends; no re-reads.
-NCU_TRAFFIC_BYTES = {'c2a': 48326912}
+NCU_TRAFFIC_BYTES = {('c2a', 1): 48326912}
 # FP32-pipe lane-cycles per (sample, neuron) row of armnet_fwd_kernel<39,1,10,1> from the same capture's executed-opcode
 # histogram (profiles/r1_v6_fwd_ncu.txt): FFMA2 409.5, FADD2 98, FMUL2 64 (2 pipe cycles each) + FADD 43 (+ a few FFMA / FMUL).
 # Used for the honest second ceiling: the path is FP32-issue bound, not HBM bound.
@@ -357,7 +357,9 @@ def main():
     abytes = algorithmic_bytes_per_sample(w) * w['bsz']
     achieved = abytes / (ms_per_step * 1e-3) / 1e9        # per GPU: one launch processes one batch
     fp32_pipe = None
-    if args.workload in NCU_FP32_PIPE_CYCLES_PER_ROW and clocks and clocks.get('sm_mhz'):
+    kind = ops.fused_fwd_kernel_kind(w['nfield'], w['nemb'], w['nhead'], w['nhid'], w['alpha'])
+    kernel_name = {1: 'armnet_fwd_kernel', 2: 'armnet_fwd_mma_kernel (E x F products as 3xTF32 warp MMAs)'}[kind]
+    if kind == 1 and args.workload in NCU_FP32_PIPE_CYCLES_PER_ROW and clocks and clocks.get('sm_mhz'):
         # warp-level FP32-pipe cycles the kernel needs per second / what 148 SMs x 4 sub-partitions offer at the sampled clock
         rows_per_s = value / n * w['nhead'] * w['nhid']
         need = rows_per_s / 32.0 * NCU_FP32_PIPE_CYCLES_PER_ROW[args.workload]   # one warp instruction serves 32 row-threads
@@ -371,11 +373,11 @@ def main():
         'config': dict(cfg, l2='flushed between timed steps (256 MiB memset outside the events)'
                        if flush is not None else 'not flushed'),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': NCU_TRAFFIC_BYTES.get(args.workload), 'peak_source': peak_src,
+                     'traffic': NCU_TRAFFIC_BYTES.get((args.workload, kind)), 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': abytes,
-                     'kernel': 'armnet_fwd_kernel (attention parameters pre-contracted once per weight version by '
+                     'kernel': kernel_name + ' (attention parameters pre-contracted once per weight version by '
                                'attn_prepare_kernel, 3.6 us, outside the per-batch step)',
-                     'note': 'path is FP32-issue/MUFU bound (entmax), not HBM bound; see DESIGN.md',
+                     'note': 'path is instruction-issue/MUFU bound (entmax), not HBM bound; see DESIGN.md',
                      'fp32_pipe': fp32_pipe},
         'e2e': {'value': w['bsz'] * args.steps * n / e2e_s, 'unit': 'samples/s',
                 'h2d_bytes_per_step': w['bsz'] * w['nfield'] * 12, 'd2h_bytes_per_step': w['bsz'] * 4,

@@ -290,3 +290,72 @@ def test_full_size_criteo_batch_properties(regime):
     tp[:, :10] = table
     z4, _ = ops.fused_forward(ids.to(d), vals.clone().to(d), tp, W, Q, Vv, 1.7, ld=12, nemb=10)
     assert torch.equal(z4, z)
+
+
+@pytest.mark.parametrize('alpha', [1.0, 1.3, 1.5, 1.7, 2.0])
+@pytest.mark.parametrize('F,scale', [(39, 0.05), (39, 3.0), (40, 1.0), (33, 1.0), (36, 8.0)])
+def test_tensor_core_kernel_matches_fp32_kernel_and_oracle(alpha, F, scale, monkeypatch):
+    """armnet_fwd_mma_kernel (the two E x F products as 3xTF32 warp MMAs; opt-in with ARMNET_MMA=1) against
+    armnet_fwd_kernel (same products on the FP32 pipe, the default) and against the oracle, for every Newton-type solver mode, padded field blocks
+    (F % 8 != 0), dense (scale 0.05) to very sparse (scale 8) gates, clamped values and both gather paths."""
+    from armnet_b200 import ops
+    from oracle import armnet_oracle as oracle
+    d = dev()
+    torch.manual_seed(1234 + F)
+    B, V, E, K, O, D = 37, 5000, 10, 2, 96, 10
+    monkeypatch.delenv('ARMNET_MMA', raising=False)
+    assert ops.fused_fwd_kernel_kind(F, E, K, O, alpha) == 1           # the tensor-core kernel is opt-in
+    monkeypatch.setenv('ARMNET_MMA', '1')
+    assert ops.fused_fwd_kernel_kind(F, E, K, O, alpha) == 2
+    assert ops.fused_fwd_kernel_kind(F, E, K, O, 2.5) == 1            # alpha > 2: the literal bisection
+    assert ops.fused_fwd_kernel_kind(F, E, K, O + 1, alpha) == 1      # K*O % 64 != 0
+    if alpha > 1.0:   # alpha == 1 is softmax whatever the solver
+        assert ops.fused_fwd_kernel_kind(F, E, K, O, alpha, ops.SOLVER_BISECT) == 1
+    ids = torch.randint(0, V, (B, F))
+    values = torch.rand(B, F) * 1.2 - 0.1                              # both clamp bounds are hit
+    table = torch.randn(V, E) * scale
+    W = torch.randn(K, E, D) * 0.5
+    Q = torch.randn(K, O, D) * 0.5
+    Vv = torch.randn(K, O, F)
+    ref = oracle.hot_path({'embedding.embedding.weight': table, 'attn_layer.bilinear_w': W, 'attn_layer.query': Q,
+                           'attn_layer.values': Vv}, alpha, ids, values.clone())
+    outs = {}
+    for kind in ('mma', 'fp32'):
+        if kind == 'fp32':
+            monkeypatch.delenv('ARMNET_MMA', raising=False)
+        else:
+            monkeypatch.setenv('ARMNET_MMA', '1')
+        for padded in (False, True):
+            tab = table.to(d)
+            ld = E
+            if padded:
+                ld = 12
+                tab = torch.zeros(V, ld, device=d)
+                tab[:, :E] = table.to(d)
+            vals = values.clone().to(d)
+            z, ex = ops.fused_forward(ids.to(d), vals, tab, W.to(d), Q.to(d), Vv.to(d), alpha, ld=ld, nemb=E,
+                                      want_tau=True, want_p=True, want_g=True, want_s=True)
+            z_plain, _ = ops.fused_forward(ids.to(d), values.clone().to(d), tab, W.to(d), Q.to(d), Vv.to(d), alpha,
+                                           ld=ld, nemb=E)
+            torch.cuda.synchronize()
+            assert torch.equal(z, z_plain)
+            assert torch.equal(vals.cpu(), values.clamp(0.001, 1.0))
+            outs[kind, padded] = (z.cpu(), {k: v.cpu() for k, v in ex.items()})
+    assert torch.equal(outs['mma', False][0], outs['mma', True][0])    # gather path does not change the result
+    # far outside the trained range (|g| up to 36) the reference's own fp32 gates move by more than 2e-6 between
+    # equivalent evaluation orders (DESIGN.md 3): the gate / sum bounds widen with |g| there, the fixtures keep 2e-6
+    wide = max(1.0, ref['g'].abs().max().item() / 4.0)
+    for key, (z, ex) in outs.items():
+        R = K * O
+        assert norm_rel(ex['g'], ref['g'].reshape(B, R, F)) <= TOL_NORM, key
+        assert (ex['p'] - ref['p'].reshape(B, R, F)).abs().max().item() <= TOL_P * wide, key
+        assert norm_rel(ex['s'], ref['s'].reshape(B, R, E)) <= TOL_NORM * wide, key
+        # z = exp(s): the reference's own fp32 rounding of s is amplified by |s|; compare in the log domain too
+        zr = ref['z'].reshape(B, R, E)
+        if zr.abs().max().item() < 1e30 and torch.isfinite(zr).all():
+            assert norm_rel(z, zr) <= TOL_NORM * max(1.0, ref['s'].abs().max().item()), key
+        assert (ex['p'].sum(-1) - 1).abs().max().item() < 1e-5, key
+    zm, zf = outs['mma', True][0], outs['fp32', True][0]
+    fin = torch.isfinite(zf) & (zf.abs() < 1e30)
+    assert torch.equal(torch.isfinite(zm), torch.isfinite(zf))
+    assert ((zm - zf)[fin].abs() <= 2e-5 * zf[fin].abs().clamp_min(1e-30) * max(1.0, ref['s'].abs().max().item())).all()
