@@ -174,8 +174,19 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
     if (!bwd) {
         if (const MmaInstance *M = select_mma_instance(I, F, E, K * O, P.ep.mode)) {
             const char *sp = getenv("ARMNET_MMA_SPLIT");
-            kernel = (sp && sp[0] == 'r') ? M->kernel_rna : M->kernel;
+            const char *wp = getenv("ARMNET_MMA_WARPS");
+            const bool dbg = out_tau || out_p || out_g || out_s;
             max_warps = kMmaWarps;
+            if (sp && sp[0] == 'r') {
+                kernel = M->kernel_rna;
+            } else if (dbg) {
+                kernel = M->kernel_dbg;
+            } else if (wp && atoi(wp) == 12) {
+                kernel = M->kernel12;
+                max_warps = 12;
+            } else {
+                kernel = M->kernel16;
+            }
         }
     }
     P.tabFP = I->FP;

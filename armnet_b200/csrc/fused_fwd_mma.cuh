@@ -161,8 +161,10 @@ __device__ __forceinline__ void solve_tau_quad(const float2 (&X)[2][NT], const E
     }
 }
 
-template <int NT, int EK, int ER, int E_STRIDE, bool RAW>
-__global__ void __launch_bounds__(kMmaWarps * 32, 1) armnet_fwd_mma_kernel(const __grid_constant__ FwdParams P) {
+// DBG: the optional outputs (out_g / out_p / out_s / out_tau) are compiled in; the plain instance has no trace of them in
+// its hot loop.  WARPS: CTA size the instance is compiled for (16 -> 128 registers per thread, 12 -> 168).
+template <int NT, int EK, int ER, int E_STRIDE, bool RAW, bool DBG, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) armnet_fwd_mma_kernel(const __grid_constant__ FwdParams P) {
     static_assert(ER == 0 || ER == 2, "leftover embedding lanes: 0 or 2");
     static_assert(8 * EK + ER <= E_STRIDE, "rows are E_STRIDE floats apart");
     constexpr int MT = 4;  // 16-row MMA steps per warp-unit (a unit = 32 row pairs, as in armnet_fwd_kernel)
@@ -308,11 +310,9 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 1) armnet_fwd_mma_kernel(const
                 split_tf32<RAW>(row0[8 * ks + g], ch[j][ks][0], cl[j][ks][0]);
                 split_tf32<RAW>(row1[8 * ks + g], ch[j][ks][1], cl[j][ks][1]);
             }
-            if (ER == 2) {
-                const float2 t0 = *reinterpret_cast<const float2 *>(row0 + 8 * EK);
-                const float2 t1 = *reinterpret_cast<const float2 *>(row1 + 8 * EK);
-                ex8[j] = make_float2(t0.x, t1.x);
-                ex9[j] = make_float2(t0.y, t1.y);
+            if (ER == 2) {  // scalar loads straight into the (f0, f1) pairs the packed ops read: no re-pairing moves
+                ex8[j] = make_float2(row0[8 * EK], row1[8 * EK]);
+                ex9[j] = make_float2(row0[8 * EK + 1], row1[8 * EK + 1]);
             } else {
                 ex8[j] = ex9[j] = make_float2(0.f, 0.f);
             }
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 1) armnet_fwd_mma_kernel(const
             }
             if (!vx) c[NT - 1][0] = c[NT - 1][2] = neg_inf();
             if (!vy) c[NT - 1][1] = c[NT - 1][3] = neg_inf();
-            if (P.out_g != nullptr) {  // validation output: g = X / (alpha-1)
+            if (DBG && P.out_g != nullptr) {  // validation output: g = X / (alpha-1)
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
 #pragma unroll
@@ -465,13 +465,13 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 1) armnet_fwd_mma_kernel(const
                     default: gates_at_tau<POW_GENERAL, NT>(X, tau, ep, G, S); break;
                 }
             }
-            if (P.out_tau != nullptr && t == 0) {
+            if (DBG && P.out_tau != nullptr && t == 0) {
                 P.out_tau[2 * grow + 0] = tau[0];
                 P.out_tau[2 * grow + 1] = S[0];
                 P.out_tau[2 * grow + 2] = tau[1];
                 P.out_tau[2 * grow + 3] = S[1];
             }
-            if (P.out_p != nullptr) {
+            if (DBG && P.out_p != nullptr) {
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
                     const int f = 8 * j + 2 * t;
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 1) armnet_fwd_mma_kernel(const
 
             // ---- s = acc / S, z = exp(s) (armnet.py:86) [then eval-mode arm_bn, armnet.py:89]
             const float inv0 = __frcp_rn(S[0]), inv1 = __frcp_rn(S[1]);  // entmax.py:63-64 renormalisation
-            if (P.out_s != nullptr) {
+            if (DBG && P.out_s != nullptr) {
 #pragma unroll
                 for (int n = 0; n < EK; ++n) {
                     float *d0 = P.out_s + grow * E + 8 * n + 2 * t;
@@ -613,11 +613,15 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 1) armnet_fwd_mma_kernel(const
 // One compiled shape of the tensor-core kernel.
 struct MmaInstance {
     int NT, EK, ER, E_STRIDE;
-    const void *kernel;      // operands split with the raw-bits form (split_tf32<true>)
-    const void *kernel_rna;  // cvt.rna.tf32 split; ARMNET_MMA_SPLIT=rna
+    const void *kernel16;      // 16 warps x 128 registers
+    const void *kernel12;      // 12 warps x 168 registers (ARMNET_MMA_WARPS=12)
+    const void *kernel_dbg;    // with the optional outputs (16 warps)
+    const void *kernel_rna;    // cvt.rna.tf32 operand split (ARMNET_MMA_SPLIT=rna), with the optional outputs
 };
-#define ARMNET_MMA_INSTANCE(NT, EK, ER, ESTR)                                             \
-    { NT, EK, ER, ESTR, (const void *)&armnet_fwd_mma_kernel<NT, EK, ER, ESTR, true>, \
-      (const void *)&armnet_fwd_mma_kernel<NT, EK, ER, ESTR, false> }
+#define ARMNET_MMA_INSTANCE(NT, EK, ER, ESTR)                                                          \
+    { NT, EK, ER, ESTR, (const void *)&armnet_fwd_mma_kernel<NT, EK, ER, ESTR, true, false, 16>, \
+      (const void *)&armnet_fwd_mma_kernel<NT, EK, ER, ESTR, true, false, 12>,                   \
+      (const void *)&armnet_fwd_mma_kernel<NT, EK, ER, ESTR, true, true, 16>,                    \
+      (const void *)&armnet_fwd_mma_kernel<NT, EK, ER, ESTR, false, true, 16> }
 
 }  // namespace armnet
