@@ -95,13 +95,15 @@ static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 // The tensor-core kernel for this shape, or null (see the requirements in fused_fwd_mma.cuh).  `I` is the
 // armnet_fwd_kernel instance of the shape: the pair tables in the workspace are laid out for it.
 static const MmaInstance *select_mma_instance(const FwdInstance *I, int F, int E, int R, int mode) {
-    // opt-in: measured on B200 at C2a it is 14 % slower than armnet_fwd_kernel (24.1 M vs 27.9 M samples/s): what the MMAs
-    // save in FFMA2s comes back as operand splits, quad shuffles and register moves (profiles/r1_v7_mma_experiment.md)
-    const char *on = getenv("ARMNET_MMA");
-    if (!on || on[0] != '1' || I->ES != 1 || R % 64 != 0 || mode == POW_BISECT) return nullptr;
+    // ARMNET_MMA=1 / 0 forces it on / off; unset: the instance's own default (on where it measured faster than
+    // armnet_fwd_kernel on B200; at C2a it is 4 % slower, 27.0 M vs 27.9 M samples/s: profiles/r1_v7_mma_experiment.md)
+    const char *env = getenv("ARMNET_MMA");
+    const int force = (env && env[0] == '1') ? 1 : (env && env[0] == '0') ? 0 : -1;
+    if (force == 0 || I->ES != 1 || R % 64 != 0 || mode == POW_BISECT) return nullptr;
     for (int i = 0; i < kNumMmaInstances; ++i) {
         const MmaInstance &M = kMmaInstances[i];
-        if (F > 8 * (M.NT - 1) && F <= 8 * M.NT && E == 8 * M.EK + M.ER && round_up(I->EC, 4) == M.E_STRIDE) return &M;
+        if (F > 8 * (M.NT - 1) && F <= 8 * M.NT && E == 8 * M.EK + M.ER && round_up(I->EC, 4) == M.E_STRIDE)
+            return (force == 1 || M.default_on) ? &M : nullptr;
     }
     return nullptr;
 }

@@ -515,8 +515,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) armnet_fwd_mma_kernel(const __g
                     a9[1] = ffma2(wr1, ex9[j], a9[1]);
                 }
             }
-            accr[0] = make_float2(quad_sum(a8[0].x + a8[0].y), quad_sum(a9[0].x + a9[0].y));
-            accr[1] = make_float2(quad_sum(a8[1].x + a8[1].y), quad_sum(a9[1].x + a9[1].y));
+            if (ER == 2) {
+                accr[0] = make_float2(quad_sum(a8[0].x + a8[0].y), quad_sum(a9[0].x + a9[0].y));
+                accr[1] = make_float2(quad_sum(a8[1].x + a8[1].y), quad_sum(a9[1].x + a9[1].y));
+            } else {
+                accr[0] = accr[1] = make_float2(0.f, 0.f);
+            }
 
             // ---- s = acc / S, z = exp(s) (armnet.py:86) [then eval-mode arm_bn, armnet.py:89]
             const float inv0 = __frcp_rn(S[0]), inv1 = __frcp_rn(S[1]);  // entmax.py:63-64 renormalisation
@@ -613,13 +617,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) armnet_fwd_mma_kernel(const __g
 // One compiled shape of the tensor-core kernel.
 struct MmaInstance {
     int NT, EK, ER, E_STRIDE;
+    int default_on;            // 1: used without ARMNET_MMA=1 (set where it measured faster than armnet_fwd_kernel)
     const void *kernel16;      // 16 warps x 128 registers
     const void *kernel12;      // 12 warps x 168 registers (ARMNET_MMA_WARPS=12)
     const void *kernel_dbg;    // with the optional outputs (16 warps)
     const void *kernel_rna;    // cvt.rna.tf32 operand split (ARMNET_MMA_SPLIT=rna), with the optional outputs
 };
-#define ARMNET_MMA_INSTANCE(NT, EK, ER, ESTR)                                                          \
-    { NT, EK, ER, ESTR, (const void *)&armnet_fwd_mma_kernel<NT, EK, ER, ESTR, true, false, 16>, \
+#define ARMNET_MMA_INSTANCE(NT, EK, ER, ESTR, ON)                                                      \
+    { NT, EK, ER, ESTR, ON, (const void *)&armnet_fwd_mma_kernel<NT, EK, ER, ESTR, true, false, 16>, \
       (const void *)&armnet_fwd_mma_kernel<NT, EK, ER, ESTR, true, false, 12>,                   \
       (const void *)&armnet_fwd_mma_kernel<NT, EK, ER, ESTR, true, true, 16>,                    \
       (const void *)&armnet_fwd_mma_kernel<NT, EK, ER, ESTR, false, true, 16> }

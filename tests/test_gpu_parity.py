@@ -295,16 +295,28 @@ def test_full_size_criteo_batch_properties(regime):
 @pytest.mark.parametrize('alpha', [1.0, 1.3, 1.5, 1.7, 2.0])
 @pytest.mark.parametrize('F,scale', [(39, 0.05), (39, 3.0), (40, 1.0), (33, 1.0), (36, 8.0)])
 def test_tensor_core_kernel_matches_fp32_kernel_and_oracle(alpha, F, scale, monkeypatch):
-    """armnet_fwd_mma_kernel (the two E x F products as 3xTF32 warp MMAs; opt-in with ARMNET_MMA=1) against
-    armnet_fwd_kernel (same products on the FP32 pipe, the default) and against the oracle, for every Newton-type solver mode, padded field blocks
-    (F % 8 != 0), dense (scale 0.05) to very sparse (scale 8) gates, clamped values and both gather paths."""
+    """armnet_fwd_mma_kernel (the two E x F products as 3xTF32 warp MMAs; ARMNET_MMA=1) against
+    armnet_fwd_kernel (same products on the FP32 pipe; ARMNET_MMA=0) and against the oracle, for every Newton-type
+    solver mode, padded field blocks (F % 8 != 0), dense (scale 0.05) to very sparse (scale 8) gates, clamped values
+    and both gather paths.  nemb 10: one MMA step + 2 leftover lanes on the FP32 pipe."""
+    _check_tensor_core_case(alpha, F, scale, 10, monkeypatch)
+
+
+@pytest.mark.parametrize('alpha', [1.0, 1.5, 1.7, 2.0])
+@pytest.mark.parametrize('F,scale', [(39, 0.05), (39, 3.0), (34, 1.0)])
+def test_tensor_core_kernel_nemb16(alpha, F, scale, monkeypatch):
+    """Same for the nemb-16 instance (config 4 shape): two MMA steps, no leftover lanes."""
+    _check_tensor_core_case(alpha, F, scale, 16, monkeypatch)
+
+
+def _check_tensor_core_case(alpha, F, scale, E, monkeypatch):
     from armnet_b200 import ops
     from oracle import armnet_oracle as oracle
     d = dev()
     torch.manual_seed(1234 + F)
-    B, V, E, K, O, D = 37, 5000, 10, 2, 96, 10
-    monkeypatch.delenv('ARMNET_MMA', raising=False)
-    assert ops.fused_fwd_kernel_kind(F, E, K, O, alpha) == 1           # the tensor-core kernel is opt-in
+    B, V, K, O, D = 37, 5000, 2, 96, 10
+    monkeypatch.setenv('ARMNET_MMA', '0')
+    assert ops.fused_fwd_kernel_kind(F, E, K, O, alpha) == 1           # forced off
     monkeypatch.setenv('ARMNET_MMA', '1')
     assert ops.fused_fwd_kernel_kind(F, E, K, O, alpha) == 2
     assert ops.fused_fwd_kernel_kind(F, E, K, O, 2.5) == 1            # alpha > 2: the literal bisection
@@ -321,15 +333,12 @@ def test_tensor_core_kernel_matches_fp32_kernel_and_oracle(alpha, F, scale, monk
                            'attn_layer.values': Vv}, alpha, ids, values.clone())
     outs = {}
     for kind in ('mma', 'fp32'):
-        if kind == 'fp32':
-            monkeypatch.delenv('ARMNET_MMA', raising=False)
-        else:
-            monkeypatch.setenv('ARMNET_MMA', '1')
+        monkeypatch.setenv('ARMNET_MMA', '0' if kind == 'fp32' else '1')
         for padded in (False, True):
             tab = table.to(d)
             ld = E
             if padded:
-                ld = 12
+                ld = E + 4 - E % 4 if E % 4 else E + 4          # 12 for nemb 10, 20 for nemb 16: 16-byte aligned rows
                 tab = torch.zeros(V, ld, device=d)
                 tab[:, :E] = table.to(d)
             vals = values.clone().to(d)

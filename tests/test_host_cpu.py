@@ -164,7 +164,8 @@ def test_fused_kernel_selection_is_host_logic(monkeypatch):
     tensor-core kernel only when opted in AND the shape / solver qualify, 0 when no instance is compiled."""
     from armnet_b200 import ops
     monkeypatch.delenv('ARMNET_MMA', raising=False)
-    assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7) == 1
+    assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7) == 1       # nemb 10: measured slower, off by default
+    assert ops.fused_fwd_kernel_kind(39, 16, 4, 128, 1.7) in (1, 2)  # per-instance default
     assert ops.fused_fwd_kernel_kind(10, 10, 1, 10, 1.7) == 1
     assert ops.fused_fwd_kernel_kind(22, 100, 1, 32, 1.5) == 1
     assert ops.fused_fwd_kernel_kind(100, 10, 4, 128, 1.7) == 0      # more than 64 fields: no instance
@@ -175,9 +176,11 @@ def test_fused_kernel_selection_is_host_logic(monkeypatch):
     assert ops.fused_fwd_kernel_kind(33, 10, 4, 64, 2.0) == 2
     assert ops.fused_fwd_kernel_kind(40, 10, 1, 64, 1.7) == 2
     assert ops.fused_fwd_kernel_kind(32, 10, 4, 128, 1.7) == 1       # field bucket not compiled
-    assert ops.fused_fwd_kernel_kind(39, 16, 4, 128, 1.7) == 1       # nemb bucket not compiled
+    assert ops.fused_fwd_kernel_kind(39, 16, 4, 128, 1.7) == 2       # nemb 16 instance (config 4)
+    assert ops.fused_fwd_kernel_kind(39, 12, 4, 128, 1.7) == 1       # nemb bucket not compiled
     assert ops.fused_fwd_kernel_kind(39, 10, 4, 100, 1.7) == 1       # K*O % 64 != 0
     assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 2.5) == 1       # alpha > 2 -> literal bisection
     assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7, ops.SOLVER_BISECT) == 1
     monkeypatch.setenv('ARMNET_MMA', '0')
     assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7) == 1
+    assert ops.fused_fwd_kernel_kind(39, 16, 4, 128, 1.7) == 1
