@@ -151,8 +151,9 @@ int armnet_fused_bwd_supported(int F, int E);
 /* Which kernel armnet_fused_fwd_f32 / armnet_fused_fwd_prepared_f32 launch for this shape (same function either way,
  * models/armnet.py:82-89): 0 = no compiled instance, 1 = armnet_fwd_kernel (both E x F products on the FP32 pipe),
  * 2 = armnet_fwd_mma_kernel (the products as warp-level TF32 tensor-core MMAs with the 3xTF32 split; needs
- * K*O % 64 == 0, a compiled field / nemb bucket and a Newton-type solver).  Kind 2 is experimental and opt-in
- * (environment ARMNET_MMA=1): parity-tested, but slower than kind 1 on B200 (profiles/r1_v7_mma_experiment.md). */
+ * K*O % 64 == 0, a compiled field / nemb bucket (33-40 fields, nemb 10 or 16) and a Newton-type solver).  Each kind-2
+ * instance is used by default only where it measured faster on B200 (nemb 16: 2.0x; nemb 10: 4 % slower, off);
+ * environment ARMNET_MMA=1 / 0 forces kind 2 / kind 1 (profiles/r1_v7_mma_experiment.md). */
 int armnet_fused_fwd_kernel_kind(int F, int E, int K, int O, float alpha, int solver);
 int armnet_fused_bwd_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V, int64_t ld,
                          const float *bilinear_w, const float *query, const float *att_values,
