@@ -12,16 +12,20 @@
 //     sum plus two quad shuffles, the element-wise work is packed f32x2 over the (f, f+1) pairs.
 //   * cross: the D fragment of the logits (now gates*values) IS the A fragment of the second MMA when k-slot t maps to
 //     field 8j+2t and k-slot t+4 to field 8j+2t+1; B = e with the same row permutation.  No shuffles, no shared memory.
-//   * tcgen05/TMEM is not used on purpose: the products are block-diagonal per sample (N = 40 columns of one sample per
-//     16..128 rows) and the gates between them need the logits in registers; the warp-level MMA keeps the whole chain
-//     in one warp's registers.  Measured issue rate on B200: 8.8 cycles per m16n8k8 per SM sub-partition
-//     (tools/ubench/mma_rate.cu), overlapping with the FP32 pipe.
+//   * Warp-level mma.sync rather than tcgen05 for this step: the products are block-diagonal per sample (N = 40 columns
+//     of one sample per 16 rows) and the gates between them need the logits in registers, so the whole chain stays in
+//     one warp's registers with no TMEM round trip.  Measured issue rate on B200: 8.8 cycles per m16n8k8 per SM
+//     sub-partition (tools/ubench/mma_rate.cu), overlapping with the FP32 pipe; the tensor pipe is ~45 % busy at nemb 16.
+//     What this formulation cannot remove is the instruction stream around the MMAs (per-thread operand splits, quad
+//     shuffles); the TMEM formulation with one row per thread is the next step and reuses this numerical core.
 //   * nemb = 8*EK + ER: EK MMA steps cover 8 embedding lanes each, the ER (0 or 2) leftover lanes are done with FP32
 //     FMAs (a whole MMA step for 2 of 8 lanes would double the tensor work at nemb = 10).
 // The MMA row i of a 16-row step is neuron 2i (i < 8) / 2(i-8)+1, so a thread's two rows are an adjacent pair: the
 // pre-contracted tables keep the row-pair layout of armnet_fwd_kernel (same workspace, same attn_prepare_kernel).
 // Requirements (checked by the host): K*O % 64 == 0 (one sample per tile, whole units), F in (8(NT-1), 8NT],
 // solver != literal bisection.  Everything else goes to armnet_fwd_kernel.
+// Measured (profiles/r1_v7_summary.md): nemb 16, 39 fields: 172 us per 4096 x 512 rows vs 346 us for armnet_fwd_kernel
+// (default there); nemb 10: 152 us vs 146 us (opt-in with ARMNET_MMA=1).
 #pragma once
 
 #include "fused_fwd.cuh"
