@@ -119,3 +119,33 @@ def test_native_parser_equals_reference_loader_on_frappe(tmp_path):
     assert skipped == 0 and ids.shape[0] == n == 3000
     assert np.array_equal(ids.astype(np.int64), ref.feat_id[:n].numpy())
     assert np.array_equal(vals, ref.feat_value[:n].numpy()) and np.array_equal(y, ref.y[:n].numpy())
+
+
+def test_parser_edge_cases(tmp_path):
+    """Empty and all-bad files, CRLF line ends, the largest id the int32 arrays hold, a single field -- same rows as
+    data_loader.py:27-47 yields.  One documented leniency: the reference's `line.split(' ')` drops a line with a doubled
+    or trailing blank (an empty token fails its `id:val` unpacking); the native parser tolerates the extra blanks."""
+    from armnet_b200.data import parse_libsvm
+
+    def write(name, text):
+        p = str(tmp_path / name)
+        with open(p, 'w', newline='') as f:
+            f.write(text)
+        return p
+
+    ids, vals, y, skipped = parse_libsvm(write('empty.libsvm', ''), 3)
+    assert ids.shape == (0, 3) and vals.shape == (0, 3) and y.shape == (0,) and skipped == 0
+    ids, vals, y, skipped = parse_libsvm(write('bad.libsvm', '\n\nfoo\n1 2:3\n'), 3)
+    assert ids.shape == (0, 3) and skipped == 4
+    p = write('crlf.libsvm', '1 1:1 2:0.5 3:1\r\n0 4:1 5:1 6:1\r\n')
+    ids, vals, y, skipped = parse_libsvm(p, 3)
+    rid, rval, ry = _python_reference_parse(p, 3)
+    assert skipped == 0 and np.array_equal(ids, rid) and np.array_equal(vals, rval) and np.array_equal(y, ry)
+    ids, vals, y, skipped = parse_libsvm(write('big.libsvm', '1 2147483647:1 0:0 7:1e-30\n'), 3)
+    assert ids.tolist() == [[2147483647, 0, 7]] and vals[0, 2] == np.float32(1e-30) and skipped == 0
+    ids, vals, y, skipped = parse_libsvm(write('one.libsvm', '0 5:2\n1 6:3\n'), 1)
+    assert ids.tolist() == [[5], [6]] and vals.tolist() == [[2.0], [3.0]] and y.tolist() == [0.0, 1.0]
+    p = write('blanks.libsvm', '1  1:1 2:1 3:1\n1 1:1 2:1 3:1 \n')
+    ids, vals, y, skipped = parse_libsvm(p, 3)
+    assert ids.shape == (2, 3) and skipped == 0                  # reference: both lines skipped
+    assert _python_reference_parse(p, 3)[0].shape == (0, 3)
