@@ -70,7 +70,9 @@ class MLP(nn.Module):
     def _fast_ok(self, x):
         return (self.tensor_core and not self.training and not torch.is_grad_enabled() and x.is_cuda
                 and x.dtype == torch.float32 and x.dim() == 2 and self.nlayers >= 1 and self.ninput % 4 == 0
-                and self.nhid % 4 == 0 and self.nhid <= 512)
+                and self.nhid % 4 == 0 and self.nhid <= 512
+                # limits of armnet_mlp_tail_f32 (csrc/mlp.cu): at most 64 outputs, a non-empty batch
+                and self.noutput <= 64 and x.shape[0] > 0)
 
     def _prepared(self):
         """(w_hi, w_lo, packed tail parameters), rebuilt when any parameter / buffer changed."""

@@ -55,12 +55,17 @@ def last_launch_count():
     return lib.armnet_last_launch_count()
 
 
-def _values_inplace(values):
+def _values_inplace(values, clamp=None, clamp_inplace=True):
     """The reference clamps the caller's tensor in place (armnet.py:82). For a contiguous fp32 tensor the kernel
-    writes into it directly; otherwise clamp with torch first and hand the kernel a contiguous copy."""
+    writes into it directly; any other layout / float dtype the reference accepts (a strided view, float64) is
+    clamped in place with torch first and the kernel gets a contiguous fp32 copy."""
     if values.dtype == torch.float32 and values.is_contiguous():
         return values, True
-    raise TypeError('values must be a contiguous float32 tensor')
+    if not values.dtype.is_floating_point:
+        raise TypeError('values must be a floating-point tensor')
+    if clamp is not None and clamp_inplace:
+        values.clamp_(clamp[0], clamp[1])
+    return values.to(torch.float32).contiguous(), False
 
 
 def embed_gather(ids, values, table, clamp: Optional[Tuple[float, float]] = None, clamp_inplace=True,
@@ -69,7 +74,7 @@ def embed_gather(ids, values, table, clamp: Optional[Tuple[float, float]] = None
     ids [B,F] int64/int32, values [B,F] f32, table [V, ld] f32 -> [B,F,E] f32 (bit-exact vs the reference)."""
     _need_cuda(ids, values, table)
     ids_c = ids.contiguous()
-    values, _ = _values_inplace(values)
+    values, _ = _values_inplace(values, clamp, clamp_inplace)
     table = _f32c(table, 'table')
     V = table.shape[0]
     ld = table.shape[1] if ld is None else ld
@@ -139,7 +144,7 @@ def fused_forward(ids, values, table, bilinear_w, query, att_values, alpha, one_
     post=(mean, scale, shift), each [K*O]: eval-mode arm_bn epilogue z <- (z - mean) * scale + shift (armnet.py:89)."""
     _need_cuda(ids, values, table, bilinear_w, query, att_values)
     ids_c = ids.contiguous()
-    values, _ = _values_inplace(values)
+    values, _ = _values_inplace(values, clamp, clamp_inplace)
     table = _f32c(table, 'table')
     W = _f32c(bilinear_w, 'bilinear_w')
     Q = _f32c(query, 'query')
@@ -471,6 +476,11 @@ class _BatchNormTrainFn(torch.autograd.Function):
             raise ValueError(f'Expected more than 1 value per channel when training, got input size {tuple(x.shape)}')
         check(rc, 'armnet_bn_train_fwd_f32')
         ctx.save_for_backward(x, weight, mean, invstd)
+        ctx.has_bias = bias is not None
+        # running statistics were written through raw pointers: bump their versions so caches keyed on them rebuild
+        written = [t for t in (running_mean, running_var) if t is not None]
+        if written:
+            torch.autograd.graph.increment_version(written)
         return out
 
     @staticmethod
@@ -486,7 +496,7 @@ class _BatchNormTrainFn(torch.autograd.Function):
                                           weight.data_ptr() if weight is not None else None, mean.data_ptr(),
                                           invstd.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(),
                                           _stream()), 'armnet_bn_train_bwd_f32')
-        return dx, (dw if weight is not None else None), (db if weight is not None else None), None, None, None, None
+        return dx, (dw if weight is not None else None), (db if ctx.has_bias else None), None, None, None, None
 
 
 def batch_norm_train(x, bn):

@@ -112,6 +112,9 @@ class FlatAdam:
         self.t += 1
         ops.clamp_adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, weight / world, self.clamp, self.lr,
                        self.betas[0], self.betas[1], self.eps, self.t)
+        # the kernel writes through raw pointers: tell torch, so every cache keyed on (data_ptr, _version) -- padded
+        # embedding table, pre-contracted attention workspace, folded arm_bn, split MLP weights -- is rebuilt
+        torch.autograd.graph.increment_version(self.params)
 
 
 @torch.no_grad()

@@ -177,3 +177,19 @@ def test_prepared_attention_workspace_equals_per_call_preparation():
         m.cache_attention = False
         y2 = m({'id': ids, 'value': vals.clone()})
     assert not torch.equal(y0, y1) and torch.equal(y1, y2)
+
+
+def test_mlp_shapes_outside_the_tail_kernel_limits_use_the_stock_path():
+    """armnet_mlp_tail_f32 handles at most 64 outputs and a non-empty batch (csrc/mlp.cu); zoo.DCNModel builds
+    MLP(..., noutput=mlp_hid) with mlp_hid = 256: such modules, and empty eval batches, must not raise."""
+    from armnet_b200.layers import MLP
+    torch.manual_seed(0)
+    m = MLP(128, 2, 128, 0.0, noutput=128).cuda().eval()
+    x = torch.randn(64, 128, device='cuda')
+    with torch.no_grad():
+        assert not m._fast_ok(x)
+        y = m(x)
+        assert torch.allclose(y, m.mlp(x))
+        m1 = MLP(128, 2, 128, 0.0, noutput=1).cuda().eval()
+        assert m1._fast_ok(x)
+        assert m1(torch.empty(0, 128, device='cuda')).shape == (0, 1)

@@ -94,8 +94,15 @@ def load_data(args):
         n = args.synthetic_rows
         return [synthetic_split(m, args.nfield, args.nfeat, args.seed + i)
                 for i, m in enumerate((n, max(n // 8, 1), max(n // 8, 1)))]
+    import glob
     d = os.path.join(args.data_dir, args.dataset)
-    return [load_libsvm(os.path.join(d, f'{s}.libsvm'), args.nfield) for s in ('train', 'valid', 'test')]
+    files = []
+    for pat in ('tr*libsvm', 'va*libsvm', 'te*libsvm'):           # data_loader.py:58-61
+        hits = sorted(glob.glob(os.path.join(d, pat)))
+        if not hits:
+            raise FileNotFoundError(f'no {pat} under {d}')
+        files.append(hits[0])
+    return [load_libsvm(f, args.nfield) for f in files]
 
 
 def batches(split, bsz, shuffle, gen):
@@ -110,32 +117,36 @@ def batches(split, bsz, shuffle, gen):
 # ------------------------------------------------------------------------------------------------ metrics
 
 def auc_on_device(logits, target):
-    """ROC-AUC of one batch by the Mann-Whitney rank statistic (ties averaged); 0 when one class is missing, like
-    utils/utils.py:104-106."""
+    """ROC-AUC of one batch by the Mann-Whitney rank statistic (ties averaged), as a 0-dim DEVICE tensor: no host
+    synchronisation. 0 when one class is missing, like utils/utils.py:104-106 (sklearn raises, the reference returns 0)."""
     pos = target > 0.5
-    n_pos = int(pos.sum())
+    n_pos = pos.sum().double()
     n_neg = target.numel() - n_pos
-    if n_pos == 0 or n_neg == 0:
-        return 0.0
     vals, inv, counts = torch.unique(logits.float(), sorted=True, return_inverse=True, return_counts=True)
     ends = torch.cumsum(counts, 0).double()
     avg_rank = ends - (counts.double() - 1) / 2
-    r_pos = avg_rank[inv][pos].sum()
-    return float((r_pos - n_pos * (n_pos + 1) / 2) / (n_pos * n_neg))
+    r_pos = (avg_rank[inv] * pos.double()).sum()
+    denom = n_pos * n_neg
+    auc = (r_pos - n_pos * (n_pos + 1) / 2) / torch.clamp(denom, min=1.0)
+    return torch.where(denom > 0, auc, torch.zeros_like(auc))
 
 
 class Meter:
+    """Running (last, weighted sum, count). Values may be 0-dim device tensors: they are accumulated on the device and
+    only read back (one synchronisation) when .val / .avg are formatted -- at report lines and at the end of a split,
+    not once per batch like the reference's loss.item() / sklearn AUC (train.py:118-122)."""
+
     def __init__(self):
         self.val = self.sum = self.cnt = 0.0
 
     def update(self, v, n=1):
         self.val = v
-        self.sum += v * n
+        self.sum = self.sum + v * n
         self.cnt += n
 
     @property
     def avg(self):
-        return self.sum / max(self.cnt, 1)
+        return float(self.sum) / max(self.cnt, 1)
 
 
 # ------------------------------------------------------------------------------------------------ loop
@@ -178,13 +189,13 @@ def run(epoch, model, split, args, plogger, dev, rank, world, optimizer=None, re
             with torch.no_grad():
                 y = model(x)
                 loss = crit(y.reshape(-1), target)
-        loss_avg.update(loss.item(), target.numel())
+        loss_avg.update(loss.detach().double(), target.numel())       # device-side accumulation, no per-batch sync
         auc_avg.update(auc_on_device(y.detach().reshape(-1), target), target.numel())
         time_avg.update(time.time() - stamp)
         stamp = time.time()
         if bi % args.report_freq == 0 and rank == 0:
             plogger.info(f'Epoch [{epoch:3d}/{args.epoch}][{bi:3d}/{(n_rows + args.batch_size - 1) // args.batch_size}]\t{time_avg.val:.3f} ({time_avg.avg:.3f}) '
-                         f'AUC {auc_avg.val:4f} ({auc_avg.avg:4f}) Loss {loss_avg.val:8.4f} ({loss_avg.avg:8.4f})')
+                         f'AUC {float(auc_avg.val):4f} ({auc_avg.avg:4f}) Loss {float(loss_avg.val):8.4f} ({loss_avg.avg:8.4f})')
         if bi >= args.eval_freq:
             break
     if rank == 0:
