@@ -21,6 +21,7 @@ SIGNATURES = {
     'armnet_version': (_I, []),
     'armnet_last_error_string': (C.c_char_p, []),
     'armnet_last_launch_count': (_I, []),
+    'armnet_set_tuning': (_I, [C.c_char_p, _I]),
     'armnet_device_info': (_I, [C.POINTER(_I), C.POINTER(_I)]),
     'armnet_embed_gather_f32': (_I, [_P, _I, _P, _P, _L, _L, _L, _I, _I, _P, _I, _F, _F, _I, _P, _P]),
     'armnet_linear_gather_f32': (_I, [_P, _I, _P, _P, _L, _L, _I, _P, _P, _P, _P]),

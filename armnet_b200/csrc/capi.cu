@@ -1,6 +1,7 @@
 // Version / error / device-info entry points and the host-side helpers shared by all entries.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -23,6 +24,33 @@ int cuda_fail(cudaError_t e, const char *what) {
 }
 
 void note_launches(int n) { g_launches = n; }
+
+static int env_int(const char *name, int unset) {
+    const char *v = getenv(name);
+    if (v == nullptr) return unset;
+    if (v[0] == '\0') return 1;
+    return atoi(v);
+}
+
+Tuning &tuning() {
+    // function-local static: initialised once (thread-safe), the environment is never read again
+    static Tuning t = [] {
+        Tuning x;
+        x.tmem = env_int("ARMNET_TMEM", -1);
+        x.mma = env_int("ARMNET_MMA", -1);
+        const char *sp = getenv("ARMNET_MMA_SPLIT");
+        x.mma_split_rna = (sp && sp[0] == 'r') ? 1 : 0;
+        x.mma_warps = env_int("ARMNET_MMA_WARPS", -1);
+        x.force_nw = env_int("ARMNET_FORCE_NW", -1);
+        x.force_look = env_int("ARMNET_FORCE_LOOK", -1);
+        x.lockstep = getenv("ARMNET_LOCKSTEP") ? 1 : 0;
+        x.no_tma_gather = getenv("ARMNET_NO_TMA_GATHER") ? 1 : 0;
+        x.no_tma_store = getenv("ARMNET_NO_TMA_STORE") ? 1 : 0;
+        x.gemm_1cta = getenv("ARMNET_GEMM_1CTA") ? 1 : 0;
+        return x;
+    }();
+    return t;
+}
 
 int get_device_info(DeviceInfo *out) {
     // Read-only cache of immutable device properties, one slot per device ordinal.
@@ -95,6 +123,23 @@ int armnet_version(void) { return ARMNET_B200_VERSION; }
 const char *armnet_last_error_string(void) { return armnet::g_err; }
 
 int armnet_last_launch_count(void) { return armnet::g_launches; }
+
+int armnet_set_tuning(const char *key, int value) {
+    if (key == nullptr) return ARMNET_ERR_NULL;
+    armnet::Tuning &t = armnet::tuning();
+    struct { const char *name; int *field; } tab[] = {
+        {"tmem", &t.tmem}, {"mma", &t.mma}, {"mma_split_rna", &t.mma_split_rna}, {"mma_warps", &t.mma_warps},
+        {"force_nw", &t.force_nw}, {"force_look", &t.force_look}, {"lockstep", &t.lockstep},
+        {"no_tma_gather", &t.no_tma_gather}, {"no_tma_store", &t.no_tma_store}, {"gemm_1cta", &t.gemm_1cta}};
+    for (auto &e : tab) {
+        if (strcmp(key, e.name) == 0) {
+            *e.field = value;
+            return ARMNET_OK;
+        }
+    }
+    armnet::set_error("armnet_set_tuning: unknown key '%s'", key);
+    return ARMNET_ERR_UNSUPPORTED;
+}
 
 int armnet_device_info(int *sm_count, int *smem_optin_bytes) {
     armnet::DeviceInfo di;

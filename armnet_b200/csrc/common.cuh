@@ -26,6 +26,22 @@ struct DeviceInfo {
 };
 int get_device_info(DeviceInfo *out);  // cached per device (read-only after first use)
 
+// Tuning / experiment switches.  Read ONCE per process from the ARMNET_* environment variables (never in a launch
+// path); armnet_set_tuning() changes them afterwards (tests, A/B runs).  -1 = the library's own default.
+struct Tuning {
+    int tmem;           // ARMNET_TMEM         1 / 0: force armnet_fwd_tmem_kernel on / off where the shape allows it
+    int mma;            // ARMNET_MMA          1 / 0: force armnet_fwd_mma_kernel on / off
+    int mma_split_rna;  // ARMNET_MMA_SPLIT=rna
+    int mma_warps;      // ARMNET_MMA_WARPS    12: the 12-warp instance
+    int force_nw;       // ARMNET_FORCE_NW     CTA size of armnet_fwd_kernel
+    int force_look;     // ARMNET_FORCE_LOOK   gather look-ahead (tiles)
+    int lockstep;       // ARMNET_LOCKSTEP
+    int no_tma_gather;  // ARMNET_NO_TMA_GATHER
+    int no_tma_store;   // ARMNET_NO_TMA_STORE
+    int gemm_1cta;      // ARMNET_GEMM_1CTA    first MLP Linear on the single-CTA kernel
+};
+Tuning &tuning();
+
 // ------------------------------------------------------------------ entmax solver parameters
 enum PowMode : int {
     POW_SOFTMAX = 0,    // alpha == 1   : p = exp(g - max)

@@ -12,6 +12,16 @@ namespace armnet {
 extern const MmaInstance kMmaInstances[];
 extern const int kNumMmaInstances;
 
+// Tensor-memory kernel (fused_fwd_tmem.cu): logits on tcgen05, the default where the shape allows it.
+bool tmem_shape_supported(int F, int E, int R);
+size_t tmem_workspace_bytes(int F, int E, int R);
+int tmem_prepare(const float *bilinear_w, const float *query, const float *att_values, int w_is_linear_layout, float am1,
+                 int F, int E, int D, int K, int O, void *workspace, cudaStream_t st);
+int tmem_launch(const char *who, const void *ids, int ids_i32, float *values, const float *table, int64_t V, int64_t ld,
+                const EntmaxParams &ep, int64_t B, int F, int E, int K, int O, int clamp, float clamp_lo, float clamp_hi,
+                int clamp_inplace, const float *post_mean, const float *post_scale, const float *post_shift, float *out_z,
+                const void *workspace, int *err_flag, cudaStream_t st);
+
 // Tables of compiled shapes, one per translation unit so they build in parallel.
 extern const FwdInstance kFwdInstancesA[];
 extern const int kNumFwdInstancesA;
@@ -97,8 +107,7 @@ static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 static const MmaInstance *select_mma_instance(const FwdInstance *I, int F, int E, int R, int mode) {
     // ARMNET_MMA=1 / 0 forces it on / off; unset: the instance's own default (on where it measured faster than
     // armnet_fwd_kernel on B200; at C2a it is 4 % slower, 27.0 M vs 27.9 M samples/s: profiles/r1_v7_mma_experiment.md)
-    const char *env = getenv("ARMNET_MMA");
-    const int force = (env && env[0] == '1') ? 1 : (env && env[0] == '0') ? 0 : -1;
+    const int force = tuning().mma;
     if (force == 0 || I->ES != 1 || R % 64 != 0 || mode == POW_BISECT) return nullptr;
     for (int i = 0; i < kNumMmaInstances; ++i) {
         const MmaInstance &M = kMmaInstances[i];
@@ -110,14 +119,26 @@ static const MmaInstance *select_mma_instance(const FwdInstance *I, int F, int E
 
 }  // namespace armnet
 
+namespace armnet {
+// Bytes of the pair tables armnet_fwd_kernel / armnet_fwd_mma_kernel read; the operands of armnet_fwd_tmem_kernel
+// follow them in the same workspace when the shape has such an instance.
+static size_t pair_tables_bytes(const FwdInstance *I, int K, int O) {
+    const size_t R2 = ((size_t)K * O + 1) / 2;
+    const size_t mstr = (size_t)(I->EC * I->ES) | 1, vstr = (size_t)I->FP | 1;
+    return (R2 * mstr * 8 + 15) / 16 * 16 + (R2 * vstr * 8 + 15) / 16 * 16;  // bulk-copy granularity
+}
+// Does this call run on armnet_fwd_tmem_kernel?  (shape, solver, 16-byte table rows, no validation outputs)
+static bool use_tmem_kernel(int F, int E, int R, int mode) {
+    return tuning().tmem != 0 && mode != POW_BISECT && tmem_shape_supported(F, E, R);
+}
+}  // namespace armnet
+
 extern "C" size_t armnet_fused_workspace_bytes(int F, int E, int K, int O) {
     using namespace armnet;
     if (F <= 0 || E <= 0 || K <= 0 || O <= 0) return 0;
     const FwdInstance *I = select_instance(F, E);
     if (!I) return 0;
-    const size_t R2 = ((size_t)K * O + 1) / 2;
-    const size_t mstr = (size_t)(I->EC * I->ES) | 1, vstr = (size_t)I->FP | 1;
-    return (R2 * mstr * 8 + 15) / 16 * 16 + (R2 * vstr * 8 + 15) / 16 * 16;  // bulk-copy granularity
+    return pair_tables_bytes(I, K, O) + tmem_workspace_bytes(F, E, K * O);
 }
 
 namespace armnet {
@@ -175,15 +196,13 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
     if (rc != ARMNET_OK) return rc;
     if (!bwd) {
         if (const MmaInstance *M = select_mma_instance(I, F, E, K * O, P.ep.mode)) {
-            const char *sp = getenv("ARMNET_MMA_SPLIT");
-            const char *wp = getenv("ARMNET_MMA_WARPS");
             const bool dbg = out_tau || out_p || out_g || out_s;
             max_warps = kMmaWarps;
-            if (sp && sp[0] == 'r') {
+            if (tuning().mma_split_rna) {
                 kernel = M->kernel_rna;
             } else if (dbg) {
                 kernel = M->kernel_dbg;
-            } else if (wp && atoi(wp) == 12) {
+            } else if (tuning().mma_warps == 12) {
                 kernel = M->kernel12;
                 max_warps = 12;
             } else {
@@ -269,19 +288,16 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
     const unsigned grid = (unsigned)(n_tiles < di.sm_count ? n_tiles : di.sm_count);
     const long long units_per_cta = (n_tiles + grid - 1) / grid * P.UPG;
     P.NW = (int)(units_per_cta < max_warps ? units_per_cta : max_warps);
-    if (const char *f = getenv("ARMNET_FORCE_NW")) {  // tuning experiments only
-        const int nw = atoi(f);
-        if (nw >= 1 && nw <= max_warps) P.NW = nw;
-    }
-    P.lockstep = getenv("ARMNET_LOCKSTEP") ? 1 : 0;  // default: units handed out dynamically
+    if (tuning().force_nw >= 1 && tuning().force_nw <= max_warps) P.NW = tuning().force_nw;  // tuning experiments only
+    P.lockstep = tuning().lockstep ? 1 : 0;  // default: units handed out dynamically
 
     // ---- TMA eligibility
     P.row_bytes = round_up(E * 4, 16);
     P.tma_gather = ((ld * 4) % 16 == 0 && (uintptr_t)table % 16 == 0 && P.row_bytes <= ld * 4) ? 1 : 0;
-    if (getenv("ARMNET_NO_TMA_GATHER")) P.tma_gather = 0;
+    if (tuning().no_tma_gather) P.tma_gather = 0;
     // a unit's output rows are contiguous when pairs never straddle samples (R even); 16-byte size/alignment of each
     // bulk store is re-checked per unit in the kernel
-    P.tma_store = (!bwd && getenv("ARMNET_NO_TMA_STORE") == nullptr && R % 2 == 0 && (uintptr_t)out_z % 16 == 0) ? 1 : 0;
+    P.tma_store = (!bwd && !tuning().no_tma_store && R % 2 == 0 && (uintptr_t)out_z % 16 == 0) ? 1 : 0;
 
     // ---- shared-memory budget: ids/values of an epoch of tiles are preloaded; the rest of the space becomes gather
     // slots (the deeper the ring, the further ahead the TMA gathers run)
@@ -311,24 +327,42 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
     if (best_slots < in_flight + 2) best_slots = in_flight + 2;
     P.n_slots = best_slots;
     P.look = P.n_slots - in_flight - 1;
-    if (const char *f = getenv("ARMNET_FORCE_LOOK")) {  // tuning experiments only
-        const int lk = atoi(f);
-        if (lk >= 1 && lk <= P.look) P.look = lk;
-    }
+    if (tuning().force_look >= 1 && tuning().force_look <= P.look) P.look = tuning().force_look;  // experiments only
     const SmemLayout L(I->FP, E_lanes, E_stride, ES, P, bwd != nullptr);
 
     cudaStream_t st = (cudaStream_t)stream;
+    // armnet_fwd_tmem_kernel: logits on tcgen05 (fused_fwd_tmem.cuh).  Its operands live after the pair tables.
+    void *tmem_ws = (char *)workspace + pair_tables_bytes(I, K, O);
+    const bool tmem_ok = tmem_shape_supported(F, E, R) && P.ep.mode != POW_BISECT;
+    const bool tmem_run = !bwd && use_tmem_kernel(F, E, R, P.ep.mode) && !out_tau && !out_p && !out_g && !out_s &&
+                          (ld * 4) % 16 == 0 && (uintptr_t)table % 16 == 0 && ((E * 4 + 15) / 16 * 16) <= ld * 4;
     if (mode != 2) {
-        const int total = R2 * (mstr + vstr) * 2;
-        int blocks = (total + 255) / 256;
-        if (blocks > di.sm_count * 4) blocks = di.sm_count * 4;
-        attn_prepare_kernel<<<blocks, 256, 0, st>>>(bilinear_w, query, att_values, w_is_linear_layout, F, E, D, O, R, R2,
-                                                     E_lanes, mstr, vstr, scale, P.ep.am1, Mg2, Vg2);
-        ARMNET_CUDA_TRY(cudaGetLastError());
+        int n_prep = 0;
+        if (mode == 1 || !tmem_run) {  // the pair tables (a mode-1 workspace must serve every kernel kind)
+            const int total = R2 * (mstr + vstr) * 2;
+            int blocks = (total + 255) / 256;
+            if (blocks > di.sm_count * 4) blocks = di.sm_count * 4;
+            attn_prepare_kernel<<<blocks, 256, 0, st>>>(bilinear_w, query, att_values, w_is_linear_layout, F, E, D, O, R,
+                                                         R2, E_lanes, mstr, vstr, scale, P.ep.am1, Mg2, Vg2);
+            ARMNET_CUDA_TRY(cudaGetLastError());
+            ++n_prep;
+        }
+        if ((mode == 1 && tmem_ok) || tmem_run) {
+            rc = tmem_prepare(bilinear_w, query, att_values, w_is_linear_layout, P.ep.am1, F, E, D, K, O, tmem_ws, st);
+            if (rc != ARMNET_OK) return rc;
+            ++n_prep;
+        }
         if (mode == 1) {
-            note_launches(1);
+            note_launches(n_prep);
             return ARMNET_OK;
         }
+    }
+    if (tmem_run) {
+        rc = tmem_launch(who, ids, ids_i32, values, table, V, ld, P.ep, B, F, E, K, O, clamp, clamp_lo, clamp_hi,
+                         clamp_inplace, post_mean, post_scale, post_shift, out_z, tmem_ws, err_flag, st);
+        if (rc != ARMNET_OK) return rc;
+        note_launches(mode == 2 ? 1 : 2);
+        return ARMNET_OK;
     }
     ARMNET_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
     void *args[] = {(void *)&P};
@@ -385,6 +419,7 @@ extern "C" int armnet_fused_fwd_kernel_kind(int F, int E, int K, int O, float al
     const FwdInstance *I = select_instance(F, E);
     EntmaxParams ep;
     if (!I || make_entmax_params(alpha, F, solver, 50, &ep) != ARMNET_OK) return 0;
+    if (use_tmem_kernel(F, E, K * O, ep.mode)) return 3;
     return select_mma_instance(I, F, E, K * O, ep.mode) ? 2 : 1;
 }
 

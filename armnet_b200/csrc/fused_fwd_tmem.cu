@@ -1,0 +1,157 @@
+// armnet_fwd_tmem_kernel (fused_fwd_tmem.cuh): compiled instances, operand preparation and launch.
+#include <math.h>
+#include <string.h>
+
+#include "fused_fwd_tmem.cuh"
+
+namespace armnet {
+
+static const TmemInstance kTmemInstances[] = {
+    ARMNET_TMEM_INSTANCE(20, 1),  // 39 fields: Criteo shape (C2a / C2b)
+    ARMNET_TMEM_INSTANCE(20, 0),  // 40 fields
+};
+
+static const TmemInstance *select_tmem_instance(int F) {
+    for (const TmemInstance &I : kTmemInstances)
+        if (F == 2 * I.NP - (I.odd ? 1 : 0)) return &I;
+    return nullptr;
+}
+
+bool tmem_shape_supported(int F, int E, int R) {
+    return select_tmem_instance(F) != nullptr && E >= 1 && E <= kTmEL && R % 256 == 0 && R >= 256 &&
+           (R / 128) * kTmKP + 2 * 4 * 2 * select_tmem_instance(F)->NP <= 512;
+}
+
+// Workspace of the TMEM kernel: Apk floats [R/128][128][32], then Vpk float2 [R/2][vstr] (16-byte padded).
+static size_t tmem_apk_bytes(int R) { return (size_t)R * kTmKP * 4; }
+static size_t tmem_vpk_bytes(int F, int R) {
+    const TmemInstance *I = select_tmem_instance(F);
+    return (((size_t)(R / 2) * (2 * I->NP + 2) * 8) + 15) / 16 * 16;
+}
+size_t tmem_workspace_bytes(int F, int E, int R) {
+    if (!tmem_shape_supported(F, E, R)) return 0;
+    return tmem_apk_bytes(R) + tmem_vpk_bytes(F, R);
+}
+
+// Apk[(kb*128 + i)*32 + k]: TMEM lane i of A block kb is neuron r = 256 (kb/2) + 64 (i/32) + 2 (i%32) + (kb%2);
+//   k in [0,10): M'[x=k][r];  [10,20): M'[x=k-10][r];  [20,30): M'[x] - trunc_tf32(M'[x]);  30, 31: 0
+//   M'[x][r] = (alpha-1) * d_k^-0.5 * sum_y W[k,x,y] Q[k,o,y]   (armnet.py:33-34, entmax.py:42; one-head: W[x,y] = W_lin[y,x])
+// Vpk[(r/2)*vstr + (r%2)*NP + j] = (V[r][2j], V[r][2j+1])                                            (armnet.py:36)
+__global__ void attn_prepare_tmem_kernel(const float *__restrict__ W, const float *__restrict__ Q,
+                                         const float *__restrict__ Vals, int lin_layout, int F, int E, int D, int O, int R,
+                                         int NP, int vstr, float scale, float am1, float *__restrict__ Apk,
+                                         float *__restrict__ Vpk) {
+    const int nA = R * kTmKP;
+    const int nV = (R / 2) * vstr * 2;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nA + nV; idx += gridDim.x * blockDim.x) {
+        if (idx < nA) {
+            const int k = idx & (kTmKP - 1), row = idx >> 5;
+            const int kb = row >> 7, i = row & 127;
+            const int r = 256 * (kb >> 1) + 64 * (i >> 5) + 2 * (i & 31) + (kb & 1);
+            const int x = k < 10 ? k : (k < 20 ? k - 10 : k - 20);
+            float a = 0.f;
+            if (k < 30 && x < E) {
+                const int kh = r / O;
+                const float *q = Q + (long long)r * D;
+                if (lin_layout) {
+                    for (int y = 0; y < D; ++y) a = fmaf(W[y * E + x], q[y], a);
+                } else {
+                    const float *w = W + ((long long)kh * E + x) * D;
+                    for (int y = 0; y < D; ++y) a = fmaf(w[y], q[y], a);
+                }
+                a = (a * scale) * am1;
+                if (k >= 20) a = a - __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+            }
+            Apk[idx] = a;
+        } else {
+            const int i2 = idx - nA;
+            const int comp = i2 & 1, q2 = i2 >> 1;       // float2 index
+            const int pair = q2 / vstr, rem = q2 - pair * vstr;
+            float v = 0.f;
+            if (rem < 2 * NP) {
+                const int n = rem / NP, j = rem - n * NP;
+                const int r = 2 * pair + n, f = 2 * j + comp;
+                if (f < F) v = Vals[(long long)r * F + f];
+            }
+            Vpk[i2] = v;
+        }
+    }
+}
+
+int tmem_prepare(const float *bilinear_w, const float *query, const float *att_values, int w_is_linear_layout, float am1,
+                 int F, int E, int D, int K, int O, void *workspace, cudaStream_t st) {
+    const int R = K * O;
+    const TmemInstance *I = select_tmem_instance(F);
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc != ARMNET_OK) return rc;
+    float *Apk = (float *)workspace;
+    float *Vpk = (float *)((char *)workspace + tmem_apk_bytes(R));
+    const int vstr = 2 * I->NP + 2;
+    const int total = R * kTmKP + (R / 2) * vstr * 2;
+    int blocks = (total + 255) / 256;
+    if (blocks > di.sm_count * 4) blocks = di.sm_count * 4;
+    const float scale = (float)pow((double)D, -0.5);  // armnet.py:15
+    attn_prepare_tmem_kernel<<<blocks, 256, 0, st>>>(bilinear_w, query, att_values, w_is_linear_layout, F, E, D, O, R, I->NP,
+                                                      vstr, scale, am1, Apk, Vpk);
+    ARMNET_CUDA_TRY(cudaGetLastError());
+    return ARMNET_OK;
+}
+
+int tmem_launch(const char *who, const void *ids, int ids_i32, float *values, const float *table, int64_t V, int64_t ld,
+                const EntmaxParams &ep, int64_t B, int F, int E, int K, int O, int clamp, float clamp_lo, float clamp_hi,
+                int clamp_inplace, const float *post_mean, const float *post_scale, const float *post_shift, float *out_z,
+                const void *workspace, int *err_flag, cudaStream_t st) {
+    const int R = K * O;
+    const TmemInstance *I = select_tmem_instance(F);
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc != ARMNET_OK) return rc;
+    TmemParams P;
+    memset(&P, 0, sizeof(P));
+    P.ids = ids;
+    P.values = values;
+    P.table = table;
+    P.Apk = (const float *)workspace;
+    P.Vpk = (const float2 *)((const char *)workspace + tmem_apk_bytes(R));
+    P.post_mean = post_mean;
+    P.post_scale = post_scale;
+    P.post_shift = post_shift;
+    P.out_z = out_z;
+    P.err_flag = err_flag;
+    P.V = V;
+    P.ld = ld;
+    P.B = B;
+    P.F = F;
+    P.E = E;
+    P.R = R;
+    P.ids_i32 = ids_i32;
+    P.clamp = clamp;
+    P.clamp_inplace = clamp_inplace;
+    P.clamp_lo = clamp_lo;
+    P.clamp_hi = clamp_hi;
+    P.ep = ep;
+    P.n_tiles = (int)((B + 1) / 2);
+    P.row_bytes = (E * 4 + 15) / 16 * 16;
+    P.tma_store = ((uintptr_t)out_z % 16 == 0) ? 1 : 0;
+    // gather look-ahead: as deep as the raw ring that fits (<= 16 tiles = 32 samples: the mbarrier block holds 32)
+    int look = 16;
+    for (; look >= 1; --look) {
+        P.look = look;
+        P.n_raw = 2 * look;
+        const TmemSmem L(I->NP, P);
+        if (L.total <= di.smem_optin) break;
+    }
+    if (look < 1) {
+        set_error("%s: F=%d E=%d K*O=%d does not fit the shared memory of the tensor-memory kernel", who, F, E, R);
+        return ARMNET_ERR_UNSUPPORTED;
+    }
+    const TmemSmem L(I->NP, P);
+    const unsigned grid = (unsigned)(P.n_tiles < di.sm_count ? P.n_tiles : di.sm_count);
+    ARMNET_CUDA_TRY(cudaFuncSetAttribute(I->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
+    void *args[] = {(void *)&P};
+    ARMNET_CUDA_TRY(cudaLaunchKernel(I->kernel, dim3(grid), dim3(kTmThreads), args, (size_t)L.total, st));
+    return ARMNET_OK;
+}
+
+}  // namespace armnet

@@ -1,0 +1,519 @@
+// Fused ARM-Net forward with the attention logits on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//   value clamp -> embedding row gather -> attention logits -> alpha-entmax gates -> gates*values
+//   -> log-space cross-feature product -> exp [-> eval-mode arm_bn]   (models/armnet.py:82-89, 26-36)
+//
+// Same function and the same C ABI entry as armnet_fwd_kernel (fused_fwd.cuh); what changes is who computes the logits
+//   X[b, r, f] = sum_x M'[x, r] e[b, f, x]       (armnet.py:33-34 with entmax.py:42's (alpha-1) folded into M'),
+// half of the FP32-pipe work of armnet_fwd_kernel.  Here they are a tcgen05.mma.kind::tf32 per (256 neurons, 2 samples):
+//   * A = rows of M'^T (M = 128 neurons per MMA), resident in TMEM for the whole kernel (written once with tcgen05.st);
+//     B = the gathered embedding rows of a TILE of two samples (N = 2 x 40 rows), in shared memory, K-major, 128-byte
+//     swizzle; D (128 lanes x 80 columns fp32) in TMEM.  Four K = 8 steps cover a "packed 3xTF32" K axis of 32:
+//         A row = [ M0..M9 | M0..M9 | m0..m9 | 0 0 ],  B row = [ e0..e9 | l0..l9 | e0..e9 | 0 0 ]
+//     with m = M - trunc_tf32(M), l = e - trunc_tf32(e): the tensor core reads the top 19 bits of an fp32 operand, so
+//     sum_k A_k B_k = sum_x (M e + M l + m e) -- fp32-grade logits (5.6e-7 norm-relative on B200,
+//     tools/ubench/tmem_logits_check.cu) from ONE accumulation chain of 4 MMAs (~45 cycles each).
+//   * TMEM lane i of the D block of A-block (2h + j) is neuron 256h + 64(i/32) + 2(i%32) + j, so a thread that reads its
+//     lane from the two blocks of an item (h) gets the two ADJACENT rows (2l, 2l+1) of the same sample as 2 x 40
+//     registers, fields packed in (f, f+1) pairs -- the layout entmax_rows.cuh works on.  The D slot is released as soon
+//     as the registers are loaded (two slots: the MMAs of the next item run under the current item's entmax).
+//   * Everything after the logits is thread-private like in armnet_fwd_kernel: entmax (entmax_rows.cuh: MUFU-free
+//     pre-solve, q-norm Newton, last sweep fused with the cross product), s[x] = sum_f p_f V_f e[f,x] on FFMA2 with the
+//     e rows read (warp-broadcast) from the B tile itself -- its first 10 floats are the exact fp32 e --, exp, optional
+//     eval-mode arm_bn, one TMA bulk store per warp-unit (64 consecutive neurons x E of one sample).
+// Roles: 12 consumer warps (3 per TMEM lane quadrant; units = (item, quadrant, sample) taken in order from one counter
+// per quadrant) + 1 producer warp: prefetches ids / values (clamp in place, range check), issues the TMA bulk row
+// gathers 8 tiles ahead into a raw ring, converts landed rows (scale by the value: e = T[id] v exactly as layers.py:21;
+// split; swizzled store), and issues the MMAs.  All hand-offs are mbarriers; no CTA-wide barrier in steady state.
+// Requirements (host-checked, everything else runs on armnet_fwd_kernel): F in {2NP-1, 2NP} for a compiled NP, E <= 10,
+// K*O a multiple of 256 and <= 768, 16-byte-aligned table rows (the module's padded shadow table), no debug outputs,
+// solver != literal bisection.
+#pragma once
+
+#include "entmax_rows.cuh"
+#include "fused_fwd.cuh"
+
+namespace armnet {
+
+constexpr int kTmConsumers = 12;                      // consumer warps (3 per TMEM lane quadrant)
+constexpr int kTmThreads = (kTmConsumers + 1) * 32;   // + the producer warp
+constexpr int kTmTiles = 4;                           // B-tile ring (tiles of 2 samples)
+constexpr int kTmKP = 32;                             // packed K (floats per operand row = 128 bytes)
+constexpr int kTmEL = 10;                             // embedding lanes of the packed layout
+
+struct TmemParams {
+    const void *ids;
+    float *values;
+    const float *table;
+    const float *Apk;         // [R/128][128][32]  packed rows of M'^T (attn_prepare_tmem_kernel)
+    const float2 *Vpk;        // [R/2][vstr]       att_values, row pairs, field-packed
+    const float *post_mean;   // [R] or null: eval-mode arm_bn, out = (z - mean) * scale + shift
+    const float *post_scale;
+    const float *post_shift;
+    float *out_z;             // [B][R][E]
+    int *err_flag;
+    long long V, ld, B;
+    int F, E, R;
+    int ids_i32;
+    int clamp, clamp_inplace;
+    float clamp_lo, clamp_hi;
+    EntmaxParams ep;
+    int n_tiles;     // ceil(B / 2)
+    int n_raw;       // raw ring depth in samples (= 2 * look)
+    int look;        // tiles of gather look-ahead
+    int row_bytes;   // bytes fetched per embedding row (multiple of 16)
+    int tma_store;
+};
+
+// Shared-memory carve-up, identical on host (sizing) and device (pointers). Offsets in bytes.
+struct TmemSmem {
+    int off_bar, off_tiles, off_V, off_raw, off_vals, off_out, total;
+    int tile_bytes, v_bytes, vstr, raw_sample_bytes, fpad, out_floats;
+    __host__ __device__ static int up(int x, int a) { return (x + a - 1) / a * a; }
+    __host__ __device__ TmemSmem(int NP, const TmemParams &P) {
+        const int NFP = 2 * NP;
+        fpad = NFP;
+        vstr = 2 * NP + 2;                 // float2 per row pair; (2 NP + 2) * 8 bytes = 16 * odd for NP = 20: LDS.128 friendly
+        tile_bytes = 2 * NFP * kTmKP * 4;  // 2 samples x NFP rows x 128 bytes (a multiple of 1024 when NFP % 8 == 0)
+        v_bytes = up((P.R / 2) * vstr * 8, 16);
+        raw_sample_bytes = up(P.F * P.row_bytes, 16);
+        out_floats = 64 * P.E;
+        off_bar = 0;                       // mbarriers + counters: 512 bytes
+        off_tiles = 1024;
+        off_V = off_tiles + kTmTiles * tile_bytes;
+        off_raw = up(off_V + v_bytes, 128);
+        off_vals = up(off_raw + P.n_raw * raw_sample_bytes, 16);
+        off_out = up(off_vals + P.n_raw * fpad * 4, 128);
+        total = off_out + (P.tma_store ? kTmConsumers * out_floats * 4 : 0);
+    }
+};
+
+// ------------------------------------------------------------------ tcgen05 wrappers (same PTX as csrc/mlp.cu)
+__device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_alloc(uint32_t *slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tm_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T   (A: 128 lanes x 8 32-bit columns at `a`)
+__device__ __forceinline__ void tm_mma_tf32_ts(uint32_t d, uint32_t a, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d),
+        "r"(a), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tm_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tm_st8(uint32_t taddr, const float (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(r[0]),
+                 "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tm_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 pairs of adjacent columns -> X[0..15] of each lane
+__device__ __forceinline__ void tm_ld32(uint32_t taddr, float2 *X) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(X[0].x), "=f"(X[0].y), "=f"(X[1].x), "=f"(X[1].y), "=f"(X[2].x), "=f"(X[2].y), "=f"(X[3].x), "=f"(X[3].y),
+          "=f"(X[4].x), "=f"(X[4].y), "=f"(X[5].x), "=f"(X[5].y), "=f"(X[6].x), "=f"(X[6].y), "=f"(X[7].x), "=f"(X[7].y),
+          "=f"(X[8].x), "=f"(X[8].y), "=f"(X[9].x), "=f"(X[9].y), "=f"(X[10].x), "=f"(X[10].y), "=f"(X[11].x),
+          "=f"(X[11].y), "=f"(X[12].x), "=f"(X[12].y), "=f"(X[13].x), "=f"(X[13].y), "=f"(X[14].x), "=f"(X[14].y),
+          "=f"(X[15].x), "=f"(X[15].y)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tm_ld8(uint32_t taddr, float2 *X) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(X[0].x), "=f"(X[0].y), "=f"(X[1].x), "=f"(X[1].y), "=f"(X[2].x), "=f"(X[2].y), "=f"(X[3].x),
+                   "=f"(X[3].y)
+                 : "r"(taddr)
+                 : "memory");
+}
+// K-major operand tile, rows of 128 bytes, SWIZZLE_128B, 8-row atoms 1024 bytes apart (csrc/mlp.cu: umma_desc_sw128)
+__device__ __forceinline__ uint64_t tm_desc_sw128(const void *tile) {
+    const uint64_t addr = (uint64_t)((smem_u32(tile) & 0x3FFFFu) >> 4);
+    return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t tm_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// Bounded mbarrier wait: a protocol bug traps (the launch fails with an error) instead of hanging the device.
+__device__ __forceinline__ void tm_wait(uint64_t *bar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    asm volatile("trap;");
+}
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// NP field pairs per row: F = 2 NP (ODD = false) or 2 NP - 1 (ODD = true).  NFP = 2 NP rows per sample in the B tile.
+template <int NP, bool ODD>
+__global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __grid_constant__ TmemParams P) {
+    constexpr int NFP = 2 * NP;
+    static_assert(NFP % 8 == 0 && 2 * NFP <= 256, "two samples of NFP rows are the N of one MMA");
+    static_assert(NP % 4 == 0 && (NP < 16 || NP >= 16), "tcgen05.ld shapes: one .x32 for 16 pairs, .x8 for every 4 more");
+    constexpr int DSLOT = 4 * NFP;  // TMEM columns of a D slot: 2 A blocks x 2 samples x NFP fields
+    constexpr int EL = kTmEL;
+    extern __shared__ __align__(1024) unsigned char smem_tm[];
+    unsigned char *smem = smem_tm;
+    const TmemSmem L(NP, P);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
+    uint64_t *bar_par = bar;                        // V table landed
+    uint64_t *d_full = bar + 1;                     // [2]  MMAs of an item done (tcgen05.commit)
+    uint64_t *d_empty = bar + 3;                    // [2]  all 8 units of an item hold their logits in registers
+    uint64_t *tile_full = bar + 5;                  // [kTmTiles]  tile converted (e rows visible to the consumers)
+    uint64_t *tile_empty = tile_full + kTmTiles;    // [kTmTiles]  every unit of the tile is done reading e
+    uint64_t *raw_full = tile_empty + kTmTiles;     // [n_raw <= 32]  gathered rows of a sample landed
+    int *next_unit = reinterpret_cast<int *>(smem + L.off_bar + 448);   // [4] one counter per lane quadrant
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.off_bar + 480);
+    unsigned char *tiles = smem + L.off_tiles;
+    const float2 *Vs = reinterpret_cast<const float2 *>(smem + L.off_V);
+    unsigned char *raw = smem + L.off_raw;
+    float *vals = reinterpret_cast<float *>(smem + L.off_vals);
+    float *outs = reinterpret_cast<float *>(smem + L.off_out);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int F = P.F, E = P.E, R = P.R;
+    const int NH = R >> 8;           // items (256 neurons) per tile
+    const int NBLK = R >> 7;         // A blocks of 128 neurons
+    const int A_COLS = NBLK * kTmKP;
+    const int G = (int)gridDim.x;
+    const int n_local = (P.n_tiles - (int)blockIdx.x + G - 1) / G;   // tiles blockIdx.x + t * G
+    const EntmaxParams ep = P.ep;
+
+    if (tid == 0) {
+        mbar_init(bar_par, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&d_full[s], 1);
+            mbar_init(&d_empty[s], 8);
+        }
+        for (int s = 0; s < kTmTiles; ++s) {
+            mbar_init(&tile_full[s], 1);
+            mbar_init(&tile_empty[s], NH * 8);
+        }
+        for (int s = 0; s < P.n_raw; ++s) mbar_init(&raw_full[s], 1);
+        for (int qd = 0; qd < 4; ++qd) next_unit[qd] = 0;
+        mbar_fence_init();
+        mbar_arrive_expect_tx(bar_par, (uint32_t)L.v_bytes);
+        tma_load_bulk(smem + L.off_V, P.Vpk, (uint32_t)L.v_bytes, bar_par);
+    }
+    if (warp == kTmConsumers) tm_alloc(tmem_slot, 512);
+    // B tiles start as zeros: the pad rows (field NFP-1 for odd F, samples past the batch) and the two pad floats of
+    // every row are never written again
+    for (int i = tid; i < kTmTiles * L.tile_bytes / 16; i += kTmThreads)
+        reinterpret_cast<float4 *>(tiles)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async_smem();
+    tm_fence_before();
+    __syncthreads();
+    tm_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // A operand: TMEM columns [0, A_COLS), lane i of block kb = packed row (kb, i)
+    if (warp < 4) {
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int kb = 0; kb < NBLK; ++kb) {
+            const float4 *src = reinterpret_cast<const float4 *>(P.Apk + ((long long)kb * 128 + warp * 32 + lane) * kTmKP);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                const float4 a = __ldg(src + 2 * c8), b = __ldg(src + 2 * c8 + 1);
+                const float r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                tm_st8(taddr + (uint32_t)(kb * kTmKP + c8 * 8), r);
+            }
+        }
+        tm_st_wait();
+    }
+    tm_fence_before();
+    __syncthreads();
+    tm_fence_after();
+    const uint32_t d_base = tmem + (uint32_t)A_COLS;
+
+    if (warp == kTmConsumers) {
+        // =========================================================== producer warp
+        const uint32_t idesc = tm_idesc_tf32(128, 2 * NFP);
+        const int rows_tile = 2 * F;          // ids / values of a tile are contiguous in the [B, F] arrays
+        constexpr int KR = (2 * NFP + 31) / 32;
+        long long pid[KR];                    // prefetched ids / clamped values of the next tile to gather
+        float pv[KR];
+        auto prefetch = [&](int t) {
+            const long long row0 = ((long long)blockIdx.x + (long long)t * G) * rows_tile;
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                const int idx = lane + 32 * k;
+                long long id = 0;
+                float v = 0.f;
+                const long long row = row0 + idx;
+                if (idx < rows_tile && t < n_local && row < P.B * F) {
+                    id = P.ids_i32 ? (long long)reinterpret_cast<const int *>(P.ids)[row]
+                                   : reinterpret_cast<const long long *>(P.ids)[row];
+                    v = P.values[row];
+                    if (P.clamp) {  // armnet.py:82 -- in place on the caller's tensor
+                        const float vc = fminf(fmaxf(v, P.clamp_lo), P.clamp_hi);
+                        if (P.clamp_inplace && vc != v) P.values[row] = vc;
+                        v = vc;
+                    }
+                    if ((unsigned long long)id >= (unsigned long long)P.V) {  // reference: IndexError (layers.py:20)
+                        if (P.err_flag) atomicOr(P.err_flag, 1);
+                        id = 0;
+                        v = 0.f;
+                    }
+                }
+                pid[k] = id;
+                pv[k] = v;
+            }
+        };
+        auto sample_valid = [&](int t, int s) {
+            return 2 * ((long long)blockIdx.x + (long long)t * G) + s < P.B;
+        };
+        // TMA bulk gather of tile t (its ids / values are in pid / pv), then prefetch the ids of tile t + 1
+        auto issue_gather = [&](int t) {
+            if (lane == 0) {
+                for (int s = 0; s < 2; ++s)
+                    if (sample_valid(t, s))
+                        mbar_arrive_expect_tx(&raw_full[(2 * t + s) % P.n_raw], (uint32_t)(F * P.row_bytes));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                const int idx = lane + 32 * k;
+                if (idx < rows_tile) {
+                    const int s = idx >= F ? 1 : 0, f = idx - s * F;
+                    if (sample_valid(t, s)) {
+                        const int rs = (2 * t + s) % P.n_raw;
+                        tma_load_bulk(raw + rs * L.raw_sample_bytes + f * P.row_bytes, P.table + pid[k] * P.ld,
+                                      (uint32_t)P.row_bytes, &raw_full[rs]);
+                        vals[rs * L.fpad + f] = pv[k];
+                    }
+                }
+            }
+            prefetch(t + 1);
+        };
+        // landed rows of tile t -> B tile: e = row * v (layers.py:21), packed [e | lo(e) | e | 0 0], 128-byte swizzle
+        auto convert = [&](int t) {
+            const int bt = t % kTmTiles;
+            if (t >= kTmTiles) tm_wait(&tile_empty[bt], (uint32_t)(t / kTmTiles - 1) & 1u);
+            for (int s = 0; s < 2; ++s)
+                if (sample_valid(t, s)) tm_wait(&raw_full[(2 * t + s) % P.n_raw], (uint32_t)((2 * t + s) / P.n_raw) & 1u);
+            unsigned char *tile = tiles + bt * L.tile_bytes;
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                const int idx = lane + 32 * k;
+                if (idx < rows_tile) {
+                    const int s = idx >= F ? 1 : 0, f = idx - s * F;
+                    if (sample_valid(t, s)) {
+                        const int rs = (2 * t + s) % P.n_raw;
+                        const float4 *src = reinterpret_cast<const float4 *>(raw + rs * L.raw_sample_bytes + f * P.row_bytes);
+                        const float v = vals[rs * L.fpad + f];
+                        float e[12], l[12];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (c * 16 < P.row_bytes) q = src[c];
+                            e[4 * c + 0] = q.x;
+                            e[4 * c + 1] = q.y;
+                            e[4 * c + 2] = q.z;
+                            e[4 * c + 3] = q.w;
+                        }
+#pragma unroll
+                        for (int x = 0; x < 12; ++x) {
+                            e[x] = (x < EL && x < E) ? __fmul_rn(e[x], v) : 0.f;
+                            l[x] = e[x] - trunc_tf32(e[x]);
+                        }
+                        const int n = s * NFP + f;
+                        float4 *dst = reinterpret_cast<float4 *>(tile + n * 128);
+                        const int sw = n & 7;
+                        dst[0 ^ sw] = make_float4(e[0], e[1], e[2], e[3]);
+                        dst[1 ^ sw] = make_float4(e[4], e[5], e[6], e[7]);
+                        dst[2 ^ sw] = make_float4(e[8], e[9], l[0], l[1]);
+                        dst[3 ^ sw] = make_float4(l[2], l[3], l[4], l[5]);
+                        dst[4 ^ sw] = make_float4(l[6], l[7], l[8], l[9]);
+                        dst[5 ^ sw] = make_float4(e[0], e[1], e[2], e[3]);
+                        dst[6 ^ sw] = make_float4(e[4], e[5], e[6], e[7]);
+                        dst[7 ^ sw] = make_float4(e[8], e[9], 0.f, 0.f);
+                    }
+                }
+            }
+            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tile_full[bt]);
+        };
+
+        prefetch(0);
+        for (int t = 0; t < P.look && t < n_local; ++t) issue_gather(t);
+        if (n_local > 0) convert(0);
+        for (int t = 0; t < n_local; ++t) {
+            if (t + P.look < n_local) issue_gather(t + P.look);
+            const uint64_t db = tm_desc_sw128(tiles + (t % kTmTiles) * L.tile_bytes);
+            for (int h = 0; h < NH; ++h) {
+                const int i = t * NH + h, slot = i & 1;
+                if (i >= 2) tm_wait(&d_empty[slot], (uint32_t)((i - 2) >> 1) & 1u);
+                tm_fence_after();
+                if (lane == 0) {
+                    const uint32_t d = d_base + (uint32_t)(slot * DSLOT);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tm_mma_tf32_ts(d + (uint32_t)(j * 2 * NFP), tmem + (uint32_t)((2 * h + j) * kTmKP + k * 8),
+                                           db + (uint64_t)(k * 32 >> 4), idesc, (uint32_t)k);
+                    tm_commit(&d_full[slot]);
+                }
+                __syncwarp();
+            }
+            if (t + 1 < n_local) convert(t + 1);
+        }
+    } else {
+        // =========================================================== consumer warps
+        const int qd = warp & 3;
+        const int n_units = n_local * NH * 2;
+        float *ost_base = outs + warp * L.out_floats;
+        tm_wait(bar_par, 0);
+        for (;;) {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(&next_unit[qd], 1);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= n_units) break;
+            const int i = u >> 1, s = u & 1;       // item, sample inside the tile
+            const int t = i / NH, h = i - t * NH;
+            const int slot = i & 1;
+            const int bt = t % kTmTiles;
+            const long long b = 2 * ((long long)blockIdx.x + (long long)t * G) + s;
+            const bool valid = b < P.B;
+
+            // ---- logits of this lane's two rows (neurons 256h + 64qd + 2 lane + {0,1}) of sample s: TMEM -> registers
+            float2 X[2][NP];
+            tm_wait(&d_full[slot], (uint32_t)(i >> 1) & 1u);
+            tm_fence_after();
+            {
+                const uint32_t ta = d_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(slot * DSLOT + s * NFP);
+#pragma unroll
+                for (int n = 0; n < 2; ++n) {
+                    const uint32_t tn = ta + (uint32_t)(n * 2 * NFP);
+                    if (NP >= 16) tm_ld32(tn, &X[n][0]);
+#pragma unroll
+                    for (int j = (NP >= 16 ? 16 : 0); j < NP; j += 4) tm_ld8(tn + 2 * j, &X[n][j]);
+                }
+                tm_ld_wait();
+            }
+            tm_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[slot]);   // the MMAs of item i + 2 may overwrite the slot
+            if (ODD) X[0][NP - 1].y = X[1][NP - 1].y = neg_inf();
+            tm_wait(&tile_full[bt], (uint32_t)(t / kTmTiles) & 1u);
+
+            float2 acc[2][EL / 2];
+            float tau[2], S[2] = {1.f, 1.f};
+            if (valid) {
+                // e rows of sample s: row n = s * NFP + f of the tile, chunk c at (c ^ (n & 7)); NFP % 8 == 0 -> n & 7 == f & 7
+                const unsigned char *eb = tiles + bt * L.tile_bytes + s * (NFP * 128);
+                const float2 *vpair = Vs + (size_t)(h * 128 + qd * 32 + lane) * L.vstr;
+                auto vrow = [&](int n, int j) -> float2 {
+                    const float4 v4 = reinterpret_cast<const float4 *>(vpair + n * NP)[j >> 1];
+                    return (j & 1) ? make_float2(v4.z, v4.w) : make_float2(v4.x, v4.y);
+                };
+                auto fma_field = [&](int f, float w0, float w1) {
+                    const unsigned char *row = eb + f * 128;
+                    const int sw = f & 7;
+                    const float4 c0 = *reinterpret_cast<const float4 *>(row + ((0 ^ sw) << 4));
+                    const float4 c1 = *reinterpret_cast<const float4 *>(row + ((1 ^ sw) << 4));
+                    const float2 c2 = *reinterpret_cast<const float2 *>(row + ((2 ^ sw) << 4));
+                    const float2 e2[EL / 2] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y),
+                                               make_float2(c1.z, c1.w), c2};
+                    const float2 a = splat2(w0), bw = splat2(w1);
+#pragma unroll
+                    for (int x = 0; x < EL / 2; ++x) {
+                        acc[0][x] = ffma2(a, e2[x], acc[0][x]);     // s[x] += w_f e[f,x]  (armnet.py:86-87)
+                        acc[1][x] = ffma2(bw, e2[x], acc[1][x]);
+                    }
+                };
+                auto cross = [&](int j, float2 w0, float2 w1) {
+                    fma_field(2 * j, w0.x, w1.x);
+                    if (!ODD || j < NP - 1) fma_field(2 * j + 1, w0.y, w1.y);
+                };
+                auto reset = [&]() {
+#pragma unroll
+                    for (int x = 0; x < EL / 2; ++x) acc[0][x] = acc[1][x] = make_float2(0.f, 0.f);
+                };
+                rows_entmax_cross<NP, ODD>(X, ep, tau, S, vrow, cross, reset);
+            }
+            // every lane is done reading the tile: hand it back (one arrival per unit)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tile_empty[bt]);
+            if (!valid) continue;
+
+            // ---- s = acc / S (entmax.py:63-64 renormalisation), z = exp(s) (armnet.py:86) [, eval-mode arm_bn, :89]
+            const int r0 = h * 256 + qd * 64 + 2 * lane;
+            float z[2][EL];
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                const float2 k2 = splat2(__frcp_rn(S[n]) * 1.4426950408889634f);
+#pragma unroll
+                for (int x = 0; x < EL / 2; ++x) {
+                    const float2 t2 = fmul2(acc[n][x], k2);
+                    z[n][2 * x] = fast_ex2(t2.x);
+                    z[n][2 * x + 1] = fast_ex2(t2.y);
+                }
+            }
+            if (P.post_scale != nullptr) {
+#pragma unroll
+                for (int n = 0; n < 2; ++n) {
+                    const float m = __ldg(P.post_mean + r0 + n), a = __ldg(P.post_scale + r0 + n),
+                                sh = __ldg(P.post_shift + r0 + n);
+#pragma unroll
+                    for (int x = 0; x < EL; ++x) z[n][x] = fmaf(z[n][x] - m, a, sh);
+                }
+            }
+            // the unit's 64 rows are contiguous in out_z: stage them, one TMA bulk store
+            float *gdst = P.out_z + ((long long)b * R + h * 256 + qd * 64) * (long long)E;
+            if (P.tma_store) {
+                if (lane == 0) tma_store_wait_read<0>();  // this warp's previous bulk store has drained the buffer
+                __syncwarp();
+                float *ost = ost_base + lane * (2 * E);
+#pragma unroll
+                for (int n = 0; n < 2; ++n)
+#pragma unroll
+                    for (int x = 0; x < EL; ++x)
+                        if (x < E) ost[n * E + x] = z[n][x];
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_bulk(gdst, ost_base, (uint32_t)(64 * E * 4));
+                    tma_store_commit();
+                }
+            } else {
+                float *dst = gdst + lane * (2 * E);
+#pragma unroll
+                for (int n = 0; n < 2; ++n)
+#pragma unroll
+                    for (int x = 0; x < EL; ++x)
+                        if (x < E) dst[n * E + x] = z[n][x];
+            }
+        }
+        if (P.tma_store && lane == 0) tma_store_wait_all<0>();
+    }
+    tm_fence_before();
+    __syncthreads();
+    if (warp == kTmConsumers) tm_dealloc(tmem, 512);
+}
+
+// One compiled shape of the kernel.
+struct TmemInstance {
+    int NP;
+    int odd;
+    const void *kernel;
+};
+#define ARMNET_TMEM_INSTANCE(NP, ODD) { NP, ODD, (const void *)&armnet_fwd_tmem_kernel<NP, (ODD) != 0> }
+
+}  // namespace armnet

@@ -839,7 +839,7 @@ static int gemm_tf32x3_impl(const float *x, int64_t B, int K, const float *w_hi,
     CUtensorMap mx, mh, ml;
     int rc;
     if ((rc = make_map(&mx, x, B, K, GM)) != ARMNET_OK) return rc;
-    const int w_box = getenv("ARMNET_GEMM_1CTA") != nullptr ? GN : GN / 2;  // the pair kernel loads W in halves
+    const int w_box = tuning().gemm_1cta != 0 ? GN : GN / 2;  // the pair kernel loads W in halves
     if ((rc = make_map(&mh, w_hi, N, K, w_box)) != ARMNET_OK) return rc;
     if ((rc = make_map(&ml, w_lo, N, K, w_box)) != ARMNET_OK) return rc;
     GemmParams P;
@@ -862,7 +862,7 @@ static int gemm_tf32x3_impl(const float *x, int64_t B, int K, const float *w_hi,
                                              G2_SMEM_BYTES));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    if (getenv("ARMNET_GEMM_1CTA") != nullptr) {  // tuning experiments only: the single-CTA (cta_group::1) kernel
+    if (tuning().gemm_1cta != 0) {  // tuning experiments only: the single-CTA (cta_group::1) kernel
         dim3 grid((unsigned)((B + GM - 1) / GM), (unsigned)((N + GN - 1) / GN), (unsigned)splits);
         mlp_gemm_tf32x3_kernel<<<grid, G_THREADS, G_SMEM_BYTES, (cudaStream_t)stream>>>(mx, mh, ml, P);
     } else {

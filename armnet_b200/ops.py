@@ -230,8 +230,32 @@ def fused_bwd_supported(F, E):
     return bool(lib.armnet_fused_bwd_supported(int(F), int(E)))
 
 
+def set_tuning(key, value):
+    """armnet_set_tuning: process-global experiment switch ('tmem', 'mma', ...; -1 = library default)."""
+    check(lib.armnet_set_tuning(key.encode(), int(value)), 'armnet_set_tuning')
+
+
+class tuning:
+    """with ops.tuning(tmem=0, mma=1): ...  -- switches restored to the library defaults (-1 / 0) on exit."""
+    _DEFAULTS = {'tmem': -1, 'mma': -1, 'mma_warps': -1, 'force_nw': -1, 'force_look': -1}
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            set_tuning(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k in self.kw:
+            set_tuning(k, self._DEFAULTS.get(k, 0))
+        return False
+
+
 def fused_fwd_kernel_kind(F, E, K, O, alpha, solver=0):
-    """0: no instance, 1: armnet_fwd_kernel (FP32 pipe), 2: armnet_fwd_mma_kernel (TF32 tensor-core products)."""
+    """0: no instance, 1: armnet_fwd_kernel (FP32 pipe), 2: armnet_fwd_mma_kernel (TF32 warp-MMA products),
+    3: armnet_fwd_tmem_kernel (logits on tcgen05 / tensor memory)."""
     return int(lib.armnet_fused_fwd_kernel_kind(int(F), int(E), int(K), int(O), float(alpha), int(solver)))
 
 

@@ -358,7 +358,8 @@ def main():
     achieved = abytes / (ms_per_step * 1e-3) / 1e9        # per GPU: one launch processes one batch
     fp32_pipe = None
     kind = ops.fused_fwd_kernel_kind(w['nfield'], w['nemb'], w['nhead'], w['nhid'], w['alpha'])
-    kernel_name = {1: 'armnet_fwd_kernel', 2: 'armnet_fwd_mma_kernel (E x F products as 3xTF32 warp MMAs)'}[kind]
+    kernel_name = {1: 'armnet_fwd_kernel', 2: 'armnet_fwd_mma_kernel (E x F products as 3xTF32 warp MMAs)',
+                   3: 'armnet_fwd_tmem_kernel (attention logits by tcgen05.mma into tensor memory)'}[kind]
     if kind == 1 and args.workload in NCU_FP32_PIPE_CYCLES_PER_ROW and clocks and clocks.get('sm_mhz'):
         # warp-level FP32-pipe cycles the kernel needs per second / what 148 SMs x 4 sub-partitions offer at the sampled clock
         rows_per_s = value / n * w['nhead'] * w['nhid']

@@ -151,9 +151,12 @@ int armnet_fused_bwd_supported(int F, int E);
 /* Which kernel armnet_fused_fwd_f32 / armnet_fused_fwd_prepared_f32 launch for this shape (same function either way,
  * models/armnet.py:82-89): 0 = no compiled instance, 1 = armnet_fwd_kernel (both E x F products on the FP32 pipe),
  * 2 = armnet_fwd_mma_kernel (the products as warp-level TF32 tensor-core MMAs with the 3xTF32 split; needs
- * K*O % 64 == 0, a compiled field / nemb bucket (33-40 fields, nemb 10 or 16) and a Newton-type solver).  Each kind-2
- * instance is used by default only where it measured faster on B200 (nemb 16: 2.0x; nemb 10: 4 % slower, off);
- * environment ARMNET_MMA=1 / 0 forces kind 2 / kind 1 (profiles/r1_v7_mma_experiment.md). */
+ * K*O % 64 == 0, a compiled field / nemb bucket (33-40 fields, nemb 10 or 16) and a Newton-type solver; default only
+ * where it measured faster on B200: nemb 16), 3 = armnet_fwd_tmem_kernel (attention logits as tcgen05.mma into tensor
+ * memory, entmax with the MUFU-free pre-solve, csrc/fused_fwd_tmem.cuh; needs 39 or 40 fields, nemb <= 10, K*O a multiple
+ * of 256 and <= 768, a Newton-type solver; at run time also 16-byte-aligned table rows and no validation outputs,
+ * otherwise the call falls back to kind 1 / 2).  armnet_set_tuning("tmem" / "mma", 1 / 0 / -1) forces a kind on / off /
+ * back to the default; the ARMNET_TMEM / ARMNET_MMA environment variables give the initial values (read once). */
 int armnet_fused_fwd_kernel_kind(int F, int E, int K, int O, float alpha, int solver);
 int armnet_fused_bwd_f32(const void *ids, int ids_i32, float *values, const float *table, int64_t V, int64_t ld,
                          const float *bilinear_w, const float *query, const float *att_values,
@@ -236,6 +239,12 @@ int armnet_libsvm_parse(const char *path, int nfield, int64_t capacity, int32_t 
 
 /* Number of kernels the last armnet_fused_fwd_f32 call on this thread launched (bench bookkeeping). */
 int armnet_last_launch_count(void);
+
+/* Tuning / experiment switches (process-global; defaults come from the ARMNET_* environment variables, which are read
+ * ONCE, at the first use, never in a launch path).  Keys: "tmem", "mma", "mma_split_rna", "mma_warps", "force_nw",
+ * "force_look", "lockstep", "no_tma_gather", "no_tma_store", "gemm_1cta".  value -1 = library default.
+ * Returns ARMNET_ERR_UNSUPPORTED for an unknown key.  Not part of the reference's surface: tests and A/B runs only. */
+int armnet_set_tuning(const char *key, int value);
 
 #ifdef __cplusplus
 }

@@ -62,7 +62,7 @@ def entmax_bisect(g: Tensor, alpha: float, n_iter: int = 50) -> Tensor:
     and 1/(alpha-1) are fp32 roundings; f_lo is never refreshed; the returned p is the one
     evaluated at the LAST midpoint tau_m (not at tau_lo) and is renormalised by its sum.
     """
-    a = torch.tensor(alpha, dtype=g.dtype).expand(*g.shape[:-1], 1)
+    a = torch.tensor(alpha, dtype=g.dtype, device=g.device).expand(*g.shape[:-1], 1)   # entmax.py:31-36
     am1 = a - 1
     inv = 1 / am1
     d = g.shape[-1]

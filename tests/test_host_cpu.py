@@ -27,7 +27,10 @@ def test_library_exports_every_declared_symbol():
 def test_argument_validation_without_gpu():
     from armnet_b200 import _capi
     lib = _capi.lib
-    assert lib.armnet_fused_workspace_bytes(39, 10, 4, 128) == 256 * (11 + 39) * 2 * 4   # row pairs x odd strides
+    # row-pair tables with odd strides, then the tensor-memory kernel's operands: 512 packed M' rows of 128 bytes and
+    # 256 field-packed value row pairs of 42 float2
+    assert lib.armnet_fused_workspace_bytes(39, 10, 4, 128) == 256 * (11 + 39) * 2 * 4 + 512 * 128 + 256 * 42 * 8
+    assert lib.armnet_fused_workspace_bytes(39, 10, 4, 100) == 200 * (11 + 39) * 2 * 4     # no tensor-memory instance
     assert lib.armnet_fused_workspace_bytes(39, 100, 1, 32) > 0
     assert lib.armnet_fused_workspace_bytes(65, 10, 4, 128) == 0        # > 64 fields: no instance
     assert lib.armnet_fused_workspace_bytes(39, 129, 4, 128) == 0
@@ -159,28 +162,45 @@ def test_training_helpers_refuse_cpu():
         BatchScorer(m, 8, 10)
 
 
-def test_fused_kernel_selection_is_host_logic(monkeypatch):
-    """armnet_fused_fwd_kernel_kind: pure host-side dispatch (no GPU): the FP32-pipe kernel by default, the
-    tensor-core kernel only when opted in AND the shape / solver qualify, 0 when no instance is compiled."""
+def test_fused_kernel_selection_is_host_logic():
+    """armnet_fused_fwd_kernel_kind: pure host-side dispatch (no GPU).  Default: the tensor-memory kernel (3) where its
+    shape constraints hold, else the FP32-pipe kernel (1) or the warp-MMA kernel (2, default at nemb 16); 0 when no
+    instance is compiled.  armnet_set_tuning switches kinds (the environment is read once per process)."""
     from armnet_b200 import ops
-    monkeypatch.delenv('ARMNET_MMA', raising=False)
-    assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7) == 1       # nemb 10: measured slower, off by default
-    assert ops.fused_fwd_kernel_kind(39, 16, 4, 128, 1.7) in (1, 2)  # per-instance default
-    assert ops.fused_fwd_kernel_kind(10, 10, 1, 10, 1.7) == 1
-    assert ops.fused_fwd_kernel_kind(22, 100, 1, 32, 1.5) == 1
-    assert ops.fused_fwd_kernel_kind(100, 10, 4, 128, 1.7) == 0      # more than 64 fields: no instance
-    assert ops.fused_fwd_kernel_kind(39, 10, 0, 128, 1.7) == 0
-    monkeypatch.setenv('ARMNET_MMA', '1')
-    for alpha in (1.0, 1.3, 1.5, 1.7, 2.0):
-        assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, alpha) == 2
-    assert ops.fused_fwd_kernel_kind(33, 10, 4, 64, 2.0) == 2
-    assert ops.fused_fwd_kernel_kind(40, 10, 1, 64, 1.7) == 2
-    assert ops.fused_fwd_kernel_kind(32, 10, 4, 128, 1.7) == 1       # field bucket not compiled
-    assert ops.fused_fwd_kernel_kind(39, 16, 4, 128, 1.7) == 2       # nemb 16 instance (config 4)
-    assert ops.fused_fwd_kernel_kind(39, 12, 4, 128, 1.7) == 1       # nemb bucket not compiled
-    assert ops.fused_fwd_kernel_kind(39, 10, 4, 100, 1.7) == 1       # K*O % 64 != 0
-    assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 2.5) == 1       # alpha > 2 -> literal bisection
-    assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7, ops.SOLVER_BISECT) == 1
-    monkeypatch.setenv('ARMNET_MMA', '0')
-    assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7) == 1
-    assert ops.fused_fwd_kernel_kind(39, 16, 4, 128, 1.7) == 1
+    try:
+        ops.set_tuning('tmem', -1)
+        ops.set_tuning('mma', -1)
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7) == 3       # C2a
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 64, 2.0) == 3        # C2b
+        assert ops.fused_fwd_kernel_kind(40, 8, 2, 128, 1.5) == 3
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 2.5) == 1       # alpha > 2 -> literal bisection
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7, ops.SOLVER_BISECT) == 1
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 100, 1.7) == 1       # K*O % 256 != 0
+        assert ops.fused_fwd_kernel_kind(39, 10, 8, 128, 1.7) == 1       # K*O = 1024: does not fit tensor memory
+        assert ops.fused_fwd_kernel_kind(38, 10, 4, 128, 1.7) == 1       # field count not compiled
+        ops.set_tuning('tmem', 0)
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7) == 1       # nemb 10 warp-MMA: measured slower, off by default
+        assert ops.fused_fwd_kernel_kind(39, 16, 4, 128, 1.7) in (1, 2)  # per-instance default
+        assert ops.fused_fwd_kernel_kind(10, 10, 1, 10, 1.7) == 1
+        assert ops.fused_fwd_kernel_kind(22, 100, 1, 32, 1.5) == 1
+        assert ops.fused_fwd_kernel_kind(100, 10, 4, 128, 1.7) == 0      # more than 64 fields: no instance
+        assert ops.fused_fwd_kernel_kind(39, 10, 0, 128, 1.7) == 0
+        ops.set_tuning('mma', 1)
+        for alpha in (1.0, 1.3, 1.5, 1.7, 2.0):
+            assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, alpha) == 2
+        assert ops.fused_fwd_kernel_kind(33, 10, 4, 64, 2.0) == 2
+        assert ops.fused_fwd_kernel_kind(40, 10, 1, 64, 1.7) == 2
+        assert ops.fused_fwd_kernel_kind(32, 10, 4, 128, 1.7) == 1       # field bucket not compiled
+        assert ops.fused_fwd_kernel_kind(39, 16, 4, 128, 1.7) == 2       # nemb 16 instance (config 4)
+        assert ops.fused_fwd_kernel_kind(39, 12, 4, 128, 1.7) == 1       # nemb bucket not compiled
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 100, 1.7) == 1       # K*O % 64 != 0
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 2.5) == 1       # alpha > 2 -> literal bisection
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7, ops.SOLVER_BISECT) == 1
+        ops.set_tuning('mma', 0)
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7) == 1
+        assert ops.fused_fwd_kernel_kind(39, 16, 4, 128, 1.7) == 1
+        with pytest.raises(Exception):
+            ops.set_tuning('no_such_switch', 1)
+    finally:
+        ops.set_tuning('tmem', -1)
+        ops.set_tuning('mma', -1)
