@@ -1,5 +1,5 @@
-// alpha-entmax threshold solvers for a thread that owns TWO rows whose F logits are packed along the FIELD axis:
-//   X[n][j] = (x[n][2j], x[n][2j+1]),  n in {0,1},  j < NP = ceil(F/2);  a padded last element (odd F) holds -inf.
+// alpha-entmax threshold solvers for a thread that owns NR rows (1 or 2) whose F logits are packed along the FIELD axis:
+//   X[n][j] = (x[n][2j], x[n][2j+1]),  n < NR,  j < NP = ceil(F/2);  a padded last element (odd F) holds -inf.
 // This is the register layout tcgen05.ld hands out (adjacent TMEM columns -> adjacent registers), so the packed f32x2
 // instructions work on (f, f+1) pairs of ONE row (entmax_pair.cuh packs the same f of TWO rows instead).
 //
@@ -28,46 +28,56 @@
 namespace armnet {
 
 // Row maxima and means.  ODD: element (NP-1).y is padding (-inf) and excluded from the mean.
-template <int NP, bool ODD>
-__device__ __forceinline__ void rows_max_mean(const float2 (&X)[2][NP], const EntmaxParams &ep, float (&mx)[2],
-                                              float (&mean)[2]) {
+template <int NR, int NP, bool ODD>
+__device__ __forceinline__ void rows_max_mean(const float2 (&X)[NR][NP], const EntmaxParams &ep, float (&mx)[NR],
+                                              float (&mean)[NR]) {
+    // two interleaved chains per reduction (even / odd pairs): the chains are latency-bound, not issue-bound
 #pragma unroll
-    for (int n = 0; n < 2; ++n) {
-        float m0 = X[n][0].x, m1 = X[n][0].y;
-        float2 s = X[n][0];
+    for (int n = 0; n < NR; ++n) {
+        float2 ma = X[n][0], mb = make_float2(neg_inf(), neg_inf());
+        float2 sa = X[n][0], sb = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 1; j < NP - 1; ++j) {
-            m0 = fmaxf(m0, X[n][j].x);
-            m1 = fmaxf(m1, X[n][j].y);
-            s = fadd2(s, X[n][j]);
-        }
-        if (NP > 1) {
-            m0 = fmaxf(m0, X[n][NP - 1].x);
-            s.x += X[n][NP - 1].x;
-            if (!ODD) {
-                m1 = fmaxf(m1, X[n][NP - 1].y);
-                s.y += X[n][NP - 1].y;
+            if (j & 1) {
+                mb = make_float2(fmaxf(mb.x, X[n][j].x), fmaxf(mb.y, X[n][j].y));
+                sb = fadd2(sb, X[n][j]);
+            } else {
+                ma = make_float2(fmaxf(ma.x, X[n][j].x), fmaxf(ma.y, X[n][j].y));
+                sa = fadd2(sa, X[n][j]);
             }
         }
-        mx[n] = fmaxf(m0, m1);
+        if (NP > 1) {
+            mb.x = fmaxf(mb.x, X[n][NP - 1].x);
+            sb.x += X[n][NP - 1].x;
+            if (!ODD) {
+                mb.y = fmaxf(mb.y, X[n][NP - 1].y);
+                sb.y += X[n][NP - 1].y;
+            }
+        }
+        const float2 s = fadd2(sa, sb);
+        mx[n] = fmaxf(fmaxf(ma.x, ma.y), fmaxf(mb.x, mb.y));
         mean[n] = (s.x + s.y) * ep.inv_F;
     }
 }
 
 // Closed-form start for near-uniform rows (entmax.cuh: entmax_uniform_start). Returns whether both rows qualify.
-template <int NP, bool ODD>
-__device__ __forceinline__ bool rows_uniform_start(const float2 (&X)[2][NP], const EntmaxParams &ep, const float (&mx)[2],
-                                                   const float (&mean)[2], float (&tau0)[2]) {
+template <int NR, int NP, bool ODD>
+__device__ __forceinline__ bool rows_uniform_start(const float2 (&X)[NR][NP], const EntmaxParams &ep, const float (&mx)[NR],
+                                                   const float (&mean)[NR], float (&tau0)[NR]) {
     bool ok = true;
 #pragma unroll
-    for (int n = 0; n < 2; ++n) {
+    for (int n = 0; n < NR; ++n) {
         const float2 nm = splat2(-mx[n]);
-        float2 sd2 = make_float2(0.f, 0.f);
+        float2 sd2 = make_float2(0.f, 0.f), sd2b = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < NP - 1; ++j) {
             const float2 d = fadd2(X[n][j], nm);
-            sd2 = ffma2(d, d, sd2);
+            if (j & 1)
+                sd2b = ffma2(d, d, sd2b);
+            else
+                sd2 = ffma2(d, d, sd2);
         }
+        sd2 = fadd2(sd2, sd2b);
         {
             const float d0 = X[n][NP - 1].x - mx[n];
             sd2.x = fmaf(d0, d0, sd2.x);
@@ -84,23 +94,88 @@ __device__ __forceinline__ bool rows_uniform_start(const float2 (&X)[2][NP], con
     return ok;
 }
 
+// Mean and variance of each row about a pivot (its first logit): no max pass, no cancellation for near-uniform rows.
+// Returns whether every row passes the near-uniform test  F var <= (0.2 cF)^2  (which bounds every |X_f - mean| by
+// 0.2 cF) and, for those, the closed-form start  tau0 = mean - cF + (q-1) var / (2 cF)  (entmax.cuh).
+template <int NR, int NP, bool ODD>
+__device__ __forceinline__ bool rows_moments_uniform(const float2 (&X)[NR][NP], const EntmaxParams &ep, float (&mean)[NR],
+                                                     float (&tau0)[NR]) {
+    bool ok = true;
+#pragma unroll
+    for (int n = 0; n < NR; ++n) {
+        const float c = X[n][0].x;
+        const float2 nc = splat2(-c);
+        float2 sa = make_float2(0.f, 0.f), sb = sa, qa = sa, qb = sa;   // two interleaved chains per sum
+#pragma unroll
+        for (int j = 0; j < NP - 1; ++j) {
+            const float2 d = fadd2(X[n][j], nc);
+            if (j & 1) {
+                sb = fadd2(sb, d);
+                qb = ffma2(d, d, qb);
+            } else {
+                sa = fadd2(sa, d);
+                qa = ffma2(d, d, qa);
+            }
+        }
+        {
+            const float d0 = X[n][NP - 1].x - c;
+            sb.x += d0;
+            qb.x = fmaf(d0, d0, qb.x);
+            if (!ODD) {
+                const float d1 = X[n][NP - 1].y - c;
+                sb.y += d1;
+                qb.y = fmaf(d1, d1, qb.y);
+            }
+        }
+        const float2 sd = fadd2(sa, sb), sq = fadd2(qa, qb);
+        const float md = (sd.x + sd.y) * ep.inv_F;
+        const float var = fmaxf(fmaf(-md, md, (sq.x + sq.y) * ep.inv_F), 0.f);
+        mean[n] = c + md;
+        tau0[n] = mean[n] - ep.cF + ep.uni_k * var;
+        ok = ok && (var <= ep.uni_var);
+    }
+    return ok;
+}
+
+// Row maxima only (the mean is known).
+template <int NR, int NP, bool ODD>
+__device__ __forceinline__ void rows_max(const float2 (&X)[NR][NP], float (&mx)[NR]) {
+#pragma unroll
+    for (int n = 0; n < NR; ++n) {
+        float2 ma = X[n][0], mb = make_float2(neg_inf(), neg_inf());
+#pragma unroll
+        for (int j = 1; j < NP - 1; ++j) {
+            if (j & 1)
+                mb = make_float2(fmaxf(mb.x, X[n][j].x), fmaxf(mb.y, X[n][j].y));
+            else
+                ma = make_float2(fmaxf(ma.x, X[n][j].x), fmaxf(ma.y, X[n][j].y));
+        }
+        if (NP > 1) {
+            mb.x = fmaxf(mb.x, X[n][NP - 1].x);
+            if (!ODD) mb.y = fmaxf(mb.y, X[n][NP - 1].y);
+        }
+        mx[n] = fmaxf(fmaxf(ma.x, ma.y), fmaxf(mb.x, mb.y));
+    }
+}
+
 // Hoelder-bound pre-solve (see the header): tau of both rows, MUFU only per row.  Valid for 1 < q < 2.
-template <int NP, int ITERS>
-__device__ __forceinline__ void rows_holder_presolve(const float2 (&X)[2][NP], const EntmaxParams &ep,
-                                                     const float (&mx)[2], const float (&mean)[2], float (&tau)[2]) {
+template <int NR, int NP, int ITERS>
+__device__ __forceinline__ void rows_holder_presolve(const float2 (&X)[NR][NP], const EntmaxParams &ep,
+                                                     const float (&mx)[NR], const float (&mean)[NR], float (&tau)[NR]) {
     const float th = 2.f - ep.q, omt = ep.q - 1.f;
 #pragma unroll
-    for (int n = 0; n < 2; ++n) tau[n] = fmaxf(mx[n] - 1.f, mean[n] - ep.cF);
+    for (int n = 0; n < NR; ++n) tau[n] = fmaxf(mx[n] - 1.f, mean[n] - ep.cF);
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
-        float2 A[2], Bq[2], C[2];
-        const float2 nt[2] = {splat2(-tau[0]), splat2(-tau[1])};
+        float2 A[NR], Bq[NR], C[NR], nt[NR];
 #pragma unroll
-        for (int n = 0; n < 2; ++n) A[n] = Bq[n] = C[n] = make_float2(0.f, 0.f);
+        for (int n = 0; n < NR; ++n) nt[n] = splat2(-tau[n]);
+#pragma unroll
+        for (int n = 0; n < NR; ++n) A[n] = Bq[n] = C[n] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
 #pragma unroll
-            for (int n = 0; n < 2; ++n) {
+            for (int n = 0; n < NR; ++n) {
                 const float2 d = fadd2(X[n][j], nt[n]);
                 const float2 u = relu2(d);
                 A[n] = fadd2(A[n], u);
@@ -109,7 +184,7 @@ __device__ __forceinline__ void rows_holder_presolve(const float2 (&X)[2][NP], c
             }
         }
 #pragma unroll
-        for (int n = 0; n < 2; ++n) {
+        for (int n = 0; n < NR; ++n) {
             const float a = fmaxf(A[n].x + A[n].y, 1e-30f), b = fmaxf(Bq[n].x + Bq[n].y, 1e-30f);
             const float c = C[n].x + C[n].y;
             const float lphi = 0.6931471805599453f * (th * fast_lg2(a) + omt * fast_lg2(b));
@@ -133,20 +208,22 @@ __device__ __forceinline__ float qnorm_newton_step(float S, float S1, const Entm
 // One evaluation sweep of both rows at tau for POW_GENERAL: S[n] = sum u^q, S1[n] = sum u^(q-1).
 // FUSED: `cross(j, w0, w1)` is called for every field pair j with w_n = (p_n[2j] V_n[2j], p_n[2j+1] V_n[2j+1]) -- the
 // caller accumulates the log-space product with them; V comes from `vrow(n, j)`.
-template <int NP, bool FUSED, class VRow, class Cross>
-__device__ __forceinline__ void rows_general_sweep(const float2 (&X)[2][NP], const float (&tau)[2],
-                                                   const EntmaxParams &ep, float (&S)[2], float (&S1)[2], VRow vrow,
+template <int NR, int NP, bool FUSED, class VRow, class Cross>
+__device__ __forceinline__ void rows_general_sweep(const float2 (&X)[NR][NP], const float (&tau)[NR],
+                                                   const EntmaxParams &ep, float (&S)[NR], float (&S1)[NR], VRow vrow,
                                                    Cross cross) {
-    const float2 nt[2] = {splat2(-tau[0]), splat2(-tau[1])};
-    const float2 qm1 = splat2(ep.qm1);
-    float2 s[2], s1[2];
+    float2 nt[NR];
 #pragma unroll
-    for (int n = 0; n < 2; ++n) s[n] = s1[n] = make_float2(0.f, 0.f);
+    for (int n = 0; n < NR; ++n) nt[n] = splat2(-tau[n]);
+    const float2 qm1 = splat2(ep.qm1);
+    float2 s[NR], s1[NR];
+#pragma unroll
+    for (int n = 0; n < NR; ++n) s[n] = s1[n] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-        float2 w[2];
+        float2 w[NR];
 #pragma unroll
-        for (int n = 0; n < 2; ++n) {
+        for (int n = 0; n < NR; ++n) {
             const float2 u = relu2(fadd2(X[n][j], nt[n]));
             const float2 t = fmul2(make_float2(fast_lg2(u.x), fast_lg2(u.y)), qm1);
             const float2 g = make_float2(fast_ex2(t.x), fast_ex2(t.y));  // u^(q-1); u = 0 -> 0 because q - 1 > 0
@@ -159,48 +236,52 @@ __device__ __forceinline__ void rows_general_sweep(const float2 (&X)[2][NP], con
                 s[n] = ffma2(g, u, s[n]);
             }
         }
-        if (FUSED) cross(j, w[0], w[1]);
+        if (FUSED) cross(j, w);
     }
 #pragma unroll
-    for (int n = 0; n < 2; ++n) {
+    for (int n = 0; n < NR; ++n) {
         S[n] = s[n].x + s[n].y;
         S1[n] = s1[n].x + s1[n].y;
     }
 }
 
 // Final pass at a solved tau for any mode: unnormalised gates, their sums, and the cross callback.
-template <int MODE, int NP, class VRow, class Cross>
-__device__ __forceinline__ void rows_cross_pass(const float2 (&X)[2][NP], const float (&tau)[2], const EntmaxParams &ep,
-                                                float (&S)[2], VRow vrow, Cross cross) {
-    const float2 nt[2] = {splat2(-tau[0]), splat2(-tau[1])};
-    float2 s[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+template <int MODE, int NR, int NP, class VRow, class Cross>
+__device__ __forceinline__ void rows_cross_pass(const float2 (&X)[NR][NP], const float (&tau)[NR], const EntmaxParams &ep,
+                                                float (&S)[NR], VRow vrow, Cross cross) {
+    float2 nt[NR], s[NR];
+#pragma unroll
+    for (int n = 0; n < NR; ++n) {
+        nt[n] = splat2(-tau[n]);
+        s[n] = make_float2(0.f, 0.f);
+    }
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-        float2 w[2];
+        float2 w[NR];
 #pragma unroll
-        for (int n = 0; n < 2; ++n) {
+        for (int n = 0; n < NR; ++n) {
             const float2 p = gate_unnorm2<MODE>(X[n][j], nt[n], ep);
             s[n] = fadd2(s[n], p);
             w[n] = fmul2(p, vrow(n, j));
         }
-        cross(j, w[0], w[1]);
+        cross(j, w);
     }
-    S[0] = s[0].x + s[0].y;
-    S[1] = s[1].x + s[1].y;
+#pragma unroll
+    for (int n = 0; n < NR; ++n) S[n] = s[n].x + s[n].y;
 }
 
 // alpha = 1.5 (u^2, u) and alpha = 2 (Michelot): the iterations of entmax.cuh on the field-packed layout.
-template <int NP>
-__device__ __forceinline__ void rows_solve_simple(const float2 (&X)[2][NP], const EntmaxParams &ep, const float (&mx)[2],
-                                                  const float (&mean)[2], float (&tau)[2]) {
+template <int NR, int NP>
+__device__ __forceinline__ void rows_solve_simple(const float2 (&X)[NR][NP], const EntmaxParams &ep, const float (&mx)[NR],
+                                                  const float (&mean)[NR], float (&tau)[NR]) {
 #pragma unroll
-    for (int n = 0; n < 2; ++n) tau[n] = fmaxf(mx[n] - 1.f, mean[n] - ep.cF);
+    for (int n = 0; n < NR; ++n) tau[n] = fmaxf(mx[n] - 1.f, mean[n] - ep.cF);
     constexpr int kMaxIt = 12;
 #pragma unroll 1
     for (int it = 0; it < kMaxIt; ++it) {
         bool done = true;
 #pragma unroll
-        for (int n = 0; n < 2; ++n) {
+        for (int n = 0; n < NR; ++n) {
             const float2 nt = splat2(-tau[n]);
             float2 s = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
             if (ep.mode == POW_SQUARE) {
@@ -235,61 +316,70 @@ __device__ __forceinline__ void rows_solve_simple(const float2 (&X)[2][NP], cons
 
 // Complete gates + cross product of two rows: solves tau, calls `reset()` before every sweep that feeds `cross`, and
 // returns S[n] (the normaliser of the gates the LAST cross sweep used).  All 32 lanes must call this together.
-template <int NP, bool ODD, class VRow, class Cross, class Reset>
-__device__ __forceinline__ void rows_entmax_cross(const float2 (&X)[2][NP], const EntmaxParams &ep, float (&tau)[2],
-                                                  float (&S)[2], VRow vrow, Cross cross, Reset reset) {
+template <int NR, int NP, bool ODD, class VRow, class Cross, class Reset>
+__device__ __forceinline__ void rows_entmax_cross(const float2 (&X)[NR][NP], const EntmaxParams &ep, float (&tau)[NR],
+                                                  float (&S)[NR], VRow vrow, Cross cross, Reset reset) {
     constexpr unsigned kFull = 0xffffffffu;
-    float mx[2], mean[2];
-    rows_max_mean<NP, ODD>(X, ep, mx, mean);
+    float mx[NR], mean[NR];
     if (ep.mode != POW_GENERAL) {
+        rows_max_mean<NR, NP, ODD>(X, ep, mx, mean);
         if (ep.mode == POW_SOFTMAX) {
-            tau[0] = mx[0];
-            tau[1] = mx[1];
+#pragma unroll
+            for (int n = 0; n < NR; ++n) tau[n] = mx[n];
         } else {
-            rows_solve_simple<NP>(X, ep, mx, mean, tau);
+            rows_solve_simple<NR, NP>(X, ep, mx, mean, tau);
         }
         reset();
         switch (ep.mode) {
-            case POW_SOFTMAX: rows_cross_pass<POW_SOFTMAX, NP>(X, tau, ep, S, vrow, cross); break;
-            case POW_LINEAR: rows_cross_pass<POW_LINEAR, NP>(X, tau, ep, S, vrow, cross); break;
-            default: rows_cross_pass<POW_SQUARE, NP>(X, tau, ep, S, vrow, cross); break;
+            case POW_SOFTMAX: rows_cross_pass<POW_SOFTMAX, NR, NP>(X, tau, ep, S, vrow, cross); break;
+            case POW_LINEAR: rows_cross_pass<POW_LINEAR, NR, NP>(X, tau, ep, S, vrow, cross); break;
+            default: rows_cross_pass<POW_SQUARE, NR, NP>(X, tau, ep, S, vrow, cross); break;
         }
         return;
     }
     // ---- POW_GENERAL
     bool fuse = false;  // warp-uniform: the next sweep also accumulates the cross product
-    if (__all_sync(kFull, fmaxf(mx[0] - mean[0], mx[1] - mean[1]) <= 0.2f * ep.cF) &&
-        __all_sync(kFull, rows_uniform_start<NP, ODD>(X, ep, mx, mean, tau))) {
+    if (__all_sync(kFull, rows_moments_uniform<NR, NP, ODD>(X, ep, mean, tau))) {
         fuse = true;  // random-init weights / weakly attending neurons: the closed form is usually exact to 1e-7
-    } else if (ep.q < 2.f) {
-        rows_holder_presolve<NP, 3>(X, ep, mx, mean, tau);
     } else {
+        rows_max<NR, NP, ODD>(X, mx);
+        if (ep.q < 2.f) {
+            rows_holder_presolve<NR, NP, 3>(X, ep, mx, mean, tau);
+        } else {
 #pragma unroll
-        for (int n = 0; n < 2; ++n) tau[n] = fmaxf(mx[n] - 1.f, mean[n] - ep.cF);
+            for (int n = 0; n < NR; ++n) tau[n] = fmaxf(mx[n] - 1.f, mean[n] - ep.cF);
+        }
     }
     constexpr int kMaxIt = 12;
-    float S1[2];
+    float S1[NR];
 #pragma unroll 1
     for (int it = 0; it < kMaxIt; ++it) {
         if (fuse) {
             reset();
-            rows_general_sweep<NP, true>(X, tau, ep, S, S1, vrow, cross);
+            rows_general_sweep<NR, NP, true>(X, tau, ep, S, S1, vrow, cross);
         } else {
-            rows_general_sweep<NP, false>(X, tau, ep, S, S1, vrow, cross);
+            rows_general_sweep<NR, NP, false>(X, tau, ep, S, S1, vrow, cross);
         }
-        const float d0 = qnorm_newton_step(S[0], S1[0], ep), d1 = qnorm_newton_step(S[1], S1[1], ep);
-        const float a0 = fabsf(d0), a1 = fabsf(d1);
-        const float rel0 = 2.4e-7f * fabsf(tau[0]), rel1 = 2.4e-7f * fabsf(tau[1]);
+        float d[NR], amax = 0.f;
+        bool tight = true, loose = true;
+#pragma unroll
+        for (int n = 0; n < NR; ++n) {
+            d[n] = qnorm_newton_step(S[n], S1[n], ep);
+            const float a = fabsf(d[n]), rel = 2.4e-7f * fabsf(tau[n]);
+            tight = tight && a <= fmaxf(5e-7f, rel);
+            loose = loose && a <= fmaxf(2e-5f, rel);
+            amax = fmaxf(amax, a);
+        }
         // |dp| <= q u^(q-1) |d| before the renormalisation: inside the parity budget (gates 2e-6 abs)
-        if (fuse && __all_sync(kFull, a0 <= fmaxf(5e-7f, rel0) && a1 <= fmaxf(5e-7f, rel1))) return;
-        tau[0] += d0;
-        tau[1] += d1;
+        if (fuse && __all_sync(kFull, tight)) return;
+#pragma unroll
+        for (int n = 0; n < NR; ++n) tau[n] += d[n];
         // the step is applied even when it is the last: |f(tau + d)| = O(d^2), and the caller renormalises
-        if (!fuse && __all_sync(kFull, a0 <= fmaxf(2e-5f, rel0) && a1 <= fmaxf(2e-5f, rel1))) break;
-        fuse = __all_sync(kFull, fmaxf(a0, a1) <= 3e-3f);
+        if (!fuse && __all_sync(kFull, loose)) break;
+        fuse = __all_sync(kFull, amax <= 3e-3f);
     }
     reset();
-    rows_cross_pass<POW_GENERAL, NP>(X, tau, ep, S, vrow, cross);
+    rows_cross_pass<POW_GENERAL, NR, NP>(X, tau, ep, S, vrow, cross);
 }
 
 }  // namespace armnet

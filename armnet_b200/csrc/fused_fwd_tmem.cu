@@ -18,36 +18,36 @@ static const TmemInstance *select_tmem_instance(int F) {
 }
 
 bool tmem_shape_supported(int F, int E, int R) {
-    return select_tmem_instance(F) != nullptr && E >= 1 && E <= kTmEL && R % 256 == 0 && R >= 256 &&
-           (R / 128) * kTmKP + 2 * 4 * 2 * select_tmem_instance(F)->NP <= 512;
+    // tensor memory: A operand (R/128 blocks x 32 columns) + 4 D slots of 2 samples x 2 NP fields
+    return select_tmem_instance(F) != nullptr && E >= 1 && E <= kTmEL && R % 128 == 0 && R >= 128 &&
+           (R / 128) * kTmKP + 4 * 4 * select_tmem_instance(F)->NP <= 512;
 }
 
-// Workspace of the TMEM kernel: Apk floats [R/128][128][32], then Vpk float2 [R/2][vstr] (16-byte padded).
+// Workspace of the TMEM kernel: Apk floats [R/128][128][32], then Vpk float2 [R][vstr] (16-byte padded).
 static size_t tmem_apk_bytes(int R) { return (size_t)R * kTmKP * 4; }
 static size_t tmem_vpk_bytes(int F, int R) {
     const TmemInstance *I = select_tmem_instance(F);
-    return (((size_t)(R / 2) * (2 * I->NP + 2) * 8) + 15) / 16 * 16;
+    return (((size_t)R * (I->NP + 2) * 8) + 15) / 16 * 16;
 }
 size_t tmem_workspace_bytes(int F, int E, int R) {
     if (!tmem_shape_supported(F, E, R)) return 0;
     return tmem_apk_bytes(R) + tmem_vpk_bytes(F, R);
 }
 
-// Apk[(kb*128 + i)*32 + k]: TMEM lane i of A block kb is neuron r = 256 (kb/2) + 64 (i/32) + 2 (i%32) + (kb%2);
+// Apk[(kb*128 + i)*32 + k]: TMEM lane i of A block kb is neuron r = 128 kb + i;
 //   k in [0,10): M'[x=k][r];  [10,20): M'[x=k-10][r];  [20,30): M'[x] - trunc_tf32(M'[x]);  30, 31: 0
 //   M'[x][r] = (alpha-1) * d_k^-0.5 * sum_y W[k,x,y] Q[k,o,y]   (armnet.py:33-34, entmax.py:42; one-head: W[x,y] = W_lin[y,x])
-// Vpk[(r/2)*vstr + (r%2)*NP + j] = (V[r][2j], V[r][2j+1])                                            (armnet.py:36)
+// Vpk[r*vstr + j] = (V[r][2j], V[r][2j+1])                                                          (armnet.py:36)
 __global__ void attn_prepare_tmem_kernel(const float *__restrict__ W, const float *__restrict__ Q,
                                          const float *__restrict__ Vals, int lin_layout, int F, int E, int D, int O, int R,
                                          int NP, int vstr, float scale, float am1, float *__restrict__ Apk,
                                          float *__restrict__ Vpk) {
     const int nA = R * kTmKP;
-    const int nV = (R / 2) * vstr * 2;
+    const int nV = R * vstr * 2;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nA + nV; idx += gridDim.x * blockDim.x) {
         if (idx < nA) {
             const int k = idx & (kTmKP - 1), row = idx >> 5;
-            const int kb = row >> 7, i = row & 127;
-            const int r = 256 * (kb >> 1) + 64 * (i >> 5) + 2 * (i & 31) + (kb & 1);
+            const int r = row;                            // = 128 kb + i
             const int x = k < 10 ? k : (k < 20 ? k - 10 : k - 20);
             float a = 0.f;
             if (k < 30 && x < E) {
@@ -66,11 +66,10 @@ __global__ void attn_prepare_tmem_kernel(const float *__restrict__ W, const floa
         } else {
             const int i2 = idx - nA;
             const int comp = i2 & 1, q2 = i2 >> 1;       // float2 index
-            const int pair = q2 / vstr, rem = q2 - pair * vstr;
+            const int r = q2 / vstr, j = q2 - r * vstr;
             float v = 0.f;
-            if (rem < 2 * NP) {
-                const int n = rem / NP, j = rem - n * NP;
-                const int r = 2 * pair + n, f = 2 * j + comp;
+            if (j < NP) {
+                const int f = 2 * j + comp;
                 if (f < F) v = Vals[(long long)r * F + f];
             }
             Vpk[i2] = v;
@@ -87,8 +86,8 @@ int tmem_prepare(const float *bilinear_w, const float *query, const float *att_v
     if (rc != ARMNET_OK) return rc;
     float *Apk = (float *)workspace;
     float *Vpk = (float *)((char *)workspace + tmem_apk_bytes(R));
-    const int vstr = 2 * I->NP + 2;
-    const int total = R * kTmKP + (R / 2) * vstr * 2;
+    const int vstr = I->NP + 2;
+    const int total = R * kTmKP + R * vstr * 2;
     int blocks = (total + 255) / 256;
     if (blocks > di.sm_count * 4) blocks = di.sm_count * 4;
     const float scale = (float)pow((double)D, -0.5);  // armnet.py:15

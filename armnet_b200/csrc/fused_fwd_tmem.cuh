@@ -21,9 +21,12 @@
 //     e rows read (warp-broadcast) from the B tile itself -- its first 10 floats are the exact fp32 e --, exp, optional
 //     eval-mode arm_bn, one TMA bulk store per warp-unit (64 consecutive neurons x E of one sample).
 // Roles: 12 consumer warps (3 per TMEM lane quadrant; units = (item, quadrant, sample) taken in order from one counter
-// per quadrant) + 1 producer warp: prefetches ids / values (clamp in place, range check), issues the TMA bulk row
-// gathers 8 tiles ahead into a raw ring, converts landed rows (scale by the value: e = T[id] v exactly as layers.py:21;
-// split; swizzled store), and issues the MMAs.  All hand-offs are mbarriers; no CTA-wide barrier in steady state.
+// per quadrant) + three producer warps that only meet through mbarriers: the GATHER warp prefetches ids / values (clamp
+// in place, range check) and issues the TMA bulk row gathers up to 16 tiles ahead into a raw ring; the CONVERT warp turns
+// landed rows into B-tile rows (scale by the value: e = T[id] v exactly as layers.py:21; split; swizzled store); the MMA
+// warp issues the tcgen05.mma of an item the moment its tile is converted and a D slot is free (a single producer warp
+// doing all three in sequence starved the consumers: 28 % issue utilisation, profiles/r2_v1_*).  No CTA-wide barrier in
+// steady state.
 // Requirements (host-checked, everything else runs on armnet_fwd_kernel): F in {2NP-1, 2NP} for a compiled NP, E <= 10,
 // K*O a multiple of 256 and <= 768, 16-byte-aligned table rows (the module's padded shadow table), no debug outputs,
 // solver != literal bisection.
@@ -34,8 +37,18 @@
 
 namespace armnet {
 
-constexpr int kTmConsumers = 12;                      // consumer warps (3 per TMEM lane quadrant)
-constexpr int kTmThreads = (kTmConsumers + 1) * 32;   // + the producer warp
+#ifndef ARMNET_TMEM_CONSUMERS
+#define ARMNET_TMEM_CONSUMERS 12
+#endif
+constexpr int kTmConsumers = ARMNET_TMEM_CONSUMERS;   // consumer warps (a multiple of 4: TMEM lane quadrants)
+#ifndef ARMNET_TMEM_SETMAXNREG
+#define ARMNET_TMEM_SETMAXNREG 0
+#endif
+// 16 warps = 12 consumers + the producer warpgroup: gather warp, convert warp, MMA warp (+ 1 idle).  4 warps per SM
+// sub-partition -> 128 registers per thread.  ARMNET_TMEM_SETMAXNREG (experiment): the producer warpgroup gives registers
+// back and the consumers grow to 160.
+constexpr int kTmWarpGather = kTmConsumers, kTmWarpConvert = kTmConsumers + 1, kTmWarpMma = kTmConsumers + 2;
+constexpr int kTmThreads = (kTmConsumers + 4) * 32;
 constexpr int kTmTiles = 4;                           // B-tile ring (tiles of 2 samples)
 constexpr int kTmKP = 32;                             // packed K (floats per operand row = 128 bytes)
 constexpr int kTmEL = 10;                             // embedding lanes of the packed layout
@@ -45,7 +58,7 @@ struct TmemParams {
     float *values;
     const float *table;
     const float *Apk;         // [R/128][128][32]  packed rows of M'^T (attn_prepare_tmem_kernel)
-    const float2 *Vpk;        // [R/2][vstr]       att_values, row pairs, field-packed
+    const float2 *Vpk;        // [R][vstr]         att_values, field-packed (f, f+1) pairs per row
     const float *post_mean;   // [R] or null: eval-mode arm_bn, out = (z - mean) * scale + shift
     const float *post_scale;
     const float *post_shift;
@@ -72,18 +85,18 @@ struct TmemSmem {
     __host__ __device__ TmemSmem(int NP, const TmemParams &P) {
         const int NFP = 2 * NP;
         fpad = NFP;
-        vstr = 2 * NP + 2;                 // float2 per row pair; (2 NP + 2) * 8 bytes = 16 * odd for NP = 20: LDS.128 friendly
+        vstr = NP + 2;                     // float2 per row; (NP + 2) * 8 bytes = 16 * odd for NP = 20: conflict-free LDS.128
         tile_bytes = 2 * NFP * kTmKP * 4;  // 2 samples x NFP rows x 128 bytes (a multiple of 1024 when NFP % 8 == 0)
-        v_bytes = up((P.R / 2) * vstr * 8, 16);
+        v_bytes = up(P.R * vstr * 8, 16);
         raw_sample_bytes = up(P.F * P.row_bytes, 16);
-        out_floats = 64 * P.E;
-        off_bar = 0;                       // mbarriers + counters: 512 bytes
+        out_floats = 32 * P.E;
+        off_bar = 0;                       // mbarriers + counters: 1024 bytes
         off_tiles = 1024;
         off_V = off_tiles + kTmTiles * tile_bytes;
         off_raw = up(off_V + v_bytes, 128);
         off_vals = up(off_raw + P.n_raw * raw_sample_bytes, 16);
         off_out = up(off_vals + P.n_raw * fpad * 4, 128);
-        total = off_out + (P.tma_store ? kTmConsumers * out_floats * 4 : 0);
+        total = off_out + (P.tma_store ? kTmConsumers * 2 * out_floats * 4 : 0);   // two staging buffers per warp
     }
 };
 
@@ -147,6 +160,7 @@ __host__ __device__ constexpr uint32_t tm_idesc_tf32(int m, int n) {
 }
 // Bounded mbarrier wait: a protocol bug traps (the launch fails with an error) instead of hanging the device.
 __device__ __forceinline__ void tm_wait(uint64_t *bar, uint32_t parity) {
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
         uint32_t ok;
         asm volatile(
@@ -164,22 +178,25 @@ __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__
 template <int NP, bool ODD>
 __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __grid_constant__ TmemParams P) {
     constexpr int NFP = 2 * NP;
-    static_assert(NFP % 8 == 0 && 2 * NFP <= 256, "two samples of NFP rows are the N of one MMA");
+    static_assert(NFP % 8 == 0 && 2 * NFP <= 256 && (2 * NFP) % 16 == 0, "two samples of NFP rows are the N of one MMA");
     static_assert(NP % 4 == 0 && (NP < 16 || NP >= 16), "tcgen05.ld shapes: one .x32 for 16 pairs, .x8 for every 4 more");
-    constexpr int DSLOT = 4 * NFP;  // TMEM columns of a D slot: 2 A blocks x 2 samples x NFP fields
+    constexpr int DSLOT = 2 * NFP;  // TMEM columns of a D slot: one A block (128 neurons) x 2 samples x NFP fields
+    constexpr int NSLOT = 4;        // D slots (A operand: <= 192 columns, 4 x 80 = 320)
     constexpr int EL = kTmEL;
     extern __shared__ __align__(1024) unsigned char smem_tm[];
     unsigned char *smem = smem_tm;
     const TmemSmem L(NP, P);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     uint64_t *bar_par = bar;                        // V table landed
-    uint64_t *d_full = bar + 1;                     // [2]  MMAs of an item done (tcgen05.commit)
-    uint64_t *d_empty = bar + 3;                    // [2]  all 8 units of an item hold their logits in registers
-    uint64_t *tile_full = bar + 5;                  // [kTmTiles]  tile converted (e rows visible to the consumers)
+    uint64_t *d_full = bar + 1;                     // [4]  MMAs of an item done (tcgen05.commit)
+    uint64_t *d_empty = bar + 5;                    // [4]  all 8 units of an item hold their logits in registers
+    uint64_t *tile_full = bar + 9;                  // [kTmTiles]  tile converted (e rows visible to the consumers)
     uint64_t *tile_empty = tile_full + kTmTiles;    // [kTmTiles]  every unit of the tile is done reading e
     uint64_t *raw_full = tile_empty + kTmTiles;     // [n_raw <= 32]  gathered rows of a sample landed
-    int *next_unit = reinterpret_cast<int *>(smem + L.off_bar + 448);   // [4] one counter per lane quadrant
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.off_bar + 480);
+    uint64_t *raw_empty = raw_full + 32;            // [n_raw <= 32]  the convert warp is done with the sample's raw rows
+    uint64_t *a_ready = raw_empty + 32;             // the A operand (M'^T) sits in tensor memory
+    int *next_unit = reinterpret_cast<int *>(smem + L.off_bar + 960);   // [4] one counter per lane quadrant
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.off_bar + 992);
     unsigned char *tiles = smem + L.off_tiles;
     const float2 *Vs = reinterpret_cast<const float2 *>(smem + L.off_V);
     unsigned char *raw = smem + L.off_raw;
@@ -188,8 +205,7 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = P.F, E = P.E, R = P.R;
-    const int NH = R >> 8;           // items (256 neurons) per tile
-    const int NBLK = R >> 7;         // A blocks of 128 neurons
+    const int NBLK = R >> 7;         // A blocks of 128 neurons = items per tile
     const int A_COLS = NBLK * kTmKP;
     const int G = (int)gridDim.x;
     const int n_local = (P.n_tiles - (int)blockIdx.x + G - 1) / G;   // tiles blockIdx.x + t * G
@@ -197,21 +213,25 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
 
     if (tid == 0) {
         mbar_init(bar_par, 1);
-        for (int s = 0; s < 2; ++s) {
+        mbar_init(a_ready, 4);
+        for (int s = 0; s < NSLOT; ++s) {
             mbar_init(&d_full[s], 1);
             mbar_init(&d_empty[s], 8);
         }
         for (int s = 0; s < kTmTiles; ++s) {
             mbar_init(&tile_full[s], 1);
-            mbar_init(&tile_empty[s], NH * 8);
+            mbar_init(&tile_empty[s], NBLK * 8);
         }
-        for (int s = 0; s < P.n_raw; ++s) mbar_init(&raw_full[s], 1);
+        for (int s = 0; s < P.n_raw; ++s) {
+            mbar_init(&raw_full[s], 1);
+            mbar_init(&raw_empty[s], 1);
+        }
         for (int qd = 0; qd < 4; ++qd) next_unit[qd] = 0;
         mbar_fence_init();
         mbar_arrive_expect_tx(bar_par, (uint32_t)L.v_bytes);
         tma_load_bulk(smem + L.off_V, P.Vpk, (uint32_t)L.v_bytes, bar_par);
     }
-    if (warp == kTmConsumers) tm_alloc(tmem_slot, 512);
+    if (warp == kTmWarpMma) tm_alloc(tmem_slot, 512);
     // B tiles start as zeros: the pad rows (field NFP-1 for odd F, samples past the batch) and the two pad floats of
     // every row are never written again
     for (int i = tid; i < kTmTiles * L.tile_bytes / 16; i += kTmThreads)
@@ -234,17 +254,25 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
             }
         }
         tm_st_wait();
+        tm_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);   // only the MMA warp waits for it: gathers and conversions start at once
     }
-    tm_fence_before();
-    __syncthreads();
-    tm_fence_after();
     const uint32_t d_base = tmem + (uint32_t)A_COLS;
 
-    if (warp == kTmConsumers) {
-        // =========================================================== producer warp
-        const uint32_t idesc = tm_idesc_tf32(128, 2 * NFP);
-        const int rows_tile = 2 * F;          // ids / values of a tile are contiguous in the [B, F] arrays
-        constexpr int KR = (2 * NFP + 31) / 32;
+#if ARMNET_TMEM_SETMAXNREG
+    if (warp >= kTmConsumers) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    }
+#endif
+    auto sample_valid = [&](int t, int s) { return 2 * ((long long)blockIdx.x + (long long)t * G) + s < P.B; };
+    const int rows_tile = 2 * F;          // ids / values of a tile are contiguous in the [B, F] arrays
+    constexpr int KR = (2 * NFP + 31) / 32;
+
+    if (warp == kTmWarpGather) {
+        // =========================================================== gather warp: ids / values -> TMA bulk row gathers
         long long pid[KR];                    // prefetched ids / clamped values of the next tile to gather
         float pv[KR];
         auto prefetch = [&](int t) {
@@ -274,16 +302,25 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
                 pv[k] = v;
             }
         };
-        auto sample_valid = [&](int t, int s) {
-            return 2 * ((long long)blockIdx.x + (long long)t * G) + s < P.B;
-        };
-        // TMA bulk gather of tile t (its ids / values are in pid / pv), then prefetch the ids of tile t + 1
-        auto issue_gather = [&](int t) {
-            if (lane == 0) {
-                for (int s = 0; s < 2; ++s)
-                    if (sample_valid(t, s))
-                        mbar_arrive_expect_tx(&raw_full[(2 * t + s) % P.n_raw], (uint32_t)(F * P.row_bytes));
+        prefetch(0);
+        for (int t = 0; t < n_local; ++t) {
+            // raw slots of tile t were last used by tile t - look: wait until the convert warp has read them
+            if (lane < 2 && sample_valid(t, lane)) {
+                const int ls = 2 * t + lane, rs = ls % P.n_raw, use = ls / P.n_raw;
+                if (use > 0) tm_wait(&raw_empty[rs], (uint32_t)(use - 1) & 1u);
             }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {   // the values first: they are published by the arrive below
+                const int idx = lane + 32 * k;
+                if (idx < rows_tile) {
+                    const int s = idx >= F ? 1 : 0, f = idx - s * F;
+                    if (sample_valid(t, s)) vals[((2 * t + s) % P.n_raw) * L.fpad + f] = pv[k];
+                }
+            }
+            __syncwarp();
+            if (lane < 2 && sample_valid(t, lane))
+                mbar_arrive_expect_tx(&raw_full[(2 * t + lane) % P.n_raw], (uint32_t)(F * P.row_bytes));
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < KR; ++k) {
@@ -294,14 +331,15 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
                         const int rs = (2 * t + s) % P.n_raw;
                         tma_load_bulk(raw + rs * L.raw_sample_bytes + f * P.row_bytes, P.table + pid[k] * P.ld,
                                       (uint32_t)P.row_bytes, &raw_full[rs]);
-                        vals[rs * L.fpad + f] = pv[k];
                     }
                 }
             }
             prefetch(t + 1);
-        };
+        }
+    } else if (warp == kTmWarpConvert) {
+        // =========================================================== convert warp
         // landed rows of tile t -> B tile: e = row * v (layers.py:21), packed [e | lo(e) | e | 0 0], 128-byte swizzle
-        auto convert = [&](int t) {
+        for (int t = 0; t < n_local; ++t) {
             const int bt = t % kTmTiles;
             if (t >= kTmTiles) tm_wait(&tile_empty[bt], (uint32_t)(t / kTmTiles - 1) & 1u);
             for (int s = 0; s < 2; ++s)
@@ -348,105 +386,106 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
             fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&tile_full[bt]);
-        };
-
-        prefetch(0);
-        for (int t = 0; t < P.look && t < n_local; ++t) issue_gather(t);
-        if (n_local > 0) convert(0);
+            if (lane < 2 && sample_valid(t, lane)) mbar_arrive(&raw_empty[(2 * t + lane) % P.n_raw]);
+        }
+    } else if (warp == kTmWarpMma) {
+        // =========================================================== MMA warp: one elected lane issues tcgen05.mma
+        const uint32_t idesc = tm_idesc_tf32(128, 2 * NFP);
+        tm_wait(a_ready, 0);
+        tm_fence_after();
         for (int t = 0; t < n_local; ++t) {
-            if (t + P.look < n_local) issue_gather(t + P.look);
-            const uint64_t db = tm_desc_sw128(tiles + (t % kTmTiles) * L.tile_bytes);
-            for (int h = 0; h < NH; ++h) {
-                const int i = t * NH + h, slot = i & 1;
-                if (i >= 2) tm_wait(&d_empty[slot], (uint32_t)((i - 2) >> 1) & 1u);
+            const int bt = t % kTmTiles;
+            tm_wait(&tile_full[bt], (uint32_t)(t / kTmTiles) & 1u);
+            const uint64_t db = tm_desc_sw128(tiles + bt * L.tile_bytes);
+            for (int kb = 0; kb < NBLK; ++kb) {
+                const int i = t * NBLK + kb, slot = i % NSLOT;
+                if (i >= NSLOT) tm_wait(&d_empty[slot], (uint32_t)(i / NSLOT - 1) & 1u);
                 tm_fence_after();
                 if (lane == 0) {
                     const uint32_t d = d_base + (uint32_t)(slot * DSLOT);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tm_mma_tf32_ts(d + (uint32_t)(j * 2 * NFP), tmem + (uint32_t)((2 * h + j) * kTmKP + k * 8),
-                                           db + (uint64_t)(k * 32 >> 4), idesc, (uint32_t)k);
+                    for (int k = 0; k < 4; ++k)
+                        tm_mma_tf32_ts(d, tmem + (uint32_t)(kb * kTmKP + k * 8), db + (uint64_t)(k * 32 >> 4), idesc,
+                                       (uint32_t)k);
                     tm_commit(&d_full[slot]);
                 }
                 __syncwarp();
             }
-            if (t + 1 < n_local) convert(t + 1);
         }
+    } else if (warp > kTmWarpMma) {
+        // idle warp of the producer warpgroup
     } else {
         // =========================================================== consumer warps
         const int qd = warp & 3;
-        const int n_units = n_local * NH * 2;
-        float *ost_base = outs + warp * L.out_floats;
+        const int n_units = n_local * NBLK * 2;
+        float *ost_warp = outs + warp * 2 * L.out_floats;
+        int obuf = 0;
         tm_wait(bar_par, 0);
+        int u_next = 0;
+        if (lane == 0) u_next = atomicAdd(&next_unit[qd], 1);
         for (;;) {
-            int u = 0;
-            if (lane == 0) u = atomicAdd(&next_unit[qd], 1);
-            u = __shfl_sync(0xffffffffu, u, 0);
+            const int u = __shfl_sync(0xffffffffu, u_next, 0);
             if (u >= n_units) break;
             const int i = u >> 1, s = u & 1;       // item, sample inside the tile
-            const int t = i / NH, h = i - t * NH;
-            const int slot = i & 1;
+            const int t = i / NBLK, kb = i - t * NBLK;
+            const int slot = i % NSLOT;
             const int bt = t % kTmTiles;
             const long long b = 2 * ((long long)blockIdx.x + (long long)t * G) + s;
             const bool valid = b < P.B;
+            const int r = kb * 128 + qd * 32 + lane;   // this lane's neuron
 
-            // ---- logits of this lane's two rows (neurons 256h + 64qd + 2 lane + {0,1}) of sample s: TMEM -> registers
-            float2 X[2][NP];
-            tm_wait(&d_full[slot], (uint32_t)(i >> 1) & 1u);
+            // ---- logits of this lane's row of sample s: TMEM -> registers, fields packed in (f, f+1) pairs
+            float2 X[1][NP];
+            tm_wait(&d_full[slot], (uint32_t)(i / NSLOT) & 1u);
             tm_fence_after();
             {
-                const uint32_t ta = d_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(slot * DSLOT + s * NFP);
+                const uint32_t tn = d_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(slot * DSLOT + s * NFP);
+                if (NP >= 16) tm_ld32(tn, &X[0][0]);
 #pragma unroll
-                for (int n = 0; n < 2; ++n) {
-                    const uint32_t tn = ta + (uint32_t)(n * 2 * NFP);
-                    if (NP >= 16) tm_ld32(tn, &X[n][0]);
-#pragma unroll
-                    for (int j = (NP >= 16 ? 16 : 0); j < NP; j += 4) tm_ld8(tn + 2 * j, &X[n][j]);
-                }
+                for (int j = (NP >= 16 ? 16 : 0); j < NP; j += 4) tm_ld8(tn + 2 * j, &X[0][j]);
                 tm_ld_wait();
             }
             tm_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&d_empty[slot]);   // the MMAs of item i + 2 may overwrite the slot
-            if (ODD) X[0][NP - 1].y = X[1][NP - 1].y = neg_inf();
+            if (lane == 0) {
+                mbar_arrive(&d_empty[slot]);               // the MMAs of item i + NSLOT may overwrite the slot
+                u_next = atomicAdd(&next_unit[qd], 1);     // claim the next unit now: the latency hides under this one
+            }
+            if (ODD) X[0][NP - 1].y = neg_inf();
             tm_wait(&tile_full[bt], (uint32_t)(t / kTmTiles) & 1u);
 
-            float2 acc[2][EL / 2];
-            float tau[2], S[2] = {1.f, 1.f};
+            float2 acc[EL / 2];
+            float tau[1], S[1] = {1.f};
             if (valid) {
                 // e rows of sample s: row n = s * NFP + f of the tile, chunk c at (c ^ (n & 7)); NFP % 8 == 0 -> n & 7 == f & 7
                 const unsigned char *eb = tiles + bt * L.tile_bytes + s * (NFP * 128);
-                const float2 *vpair = Vs + (size_t)(h * 128 + qd * 32 + lane) * L.vstr;
-                auto vrow = [&](int n, int j) -> float2 {
-                    const float4 v4 = reinterpret_cast<const float4 *>(vpair + n * NP)[j >> 1];
+                const float4 *vr = reinterpret_cast<const float4 *>(Vs + (size_t)r * L.vstr);
+                auto vrow = [&](int, int j) -> float2 {
+                    const float4 v4 = vr[j >> 1];
                     return (j & 1) ? make_float2(v4.z, v4.w) : make_float2(v4.x, v4.y);
                 };
-                auto fma_field = [&](int f, float w0, float w1) {
+                auto fma_field = [&](int f, float w) {
                     const unsigned char *row = eb + f * 128;
                     const int sw = f & 7;
                     const float4 c0 = *reinterpret_cast<const float4 *>(row + ((0 ^ sw) << 4));
                     const float4 c1 = *reinterpret_cast<const float4 *>(row + ((1 ^ sw) << 4));
                     const float2 c2 = *reinterpret_cast<const float2 *>(row + ((2 ^ sw) << 4));
-                    const float2 e2[EL / 2] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y),
-                                               make_float2(c1.z, c1.w), c2};
-                    const float2 a = splat2(w0), bw = splat2(w1);
-#pragma unroll
-                    for (int x = 0; x < EL / 2; ++x) {
-                        acc[0][x] = ffma2(a, e2[x], acc[0][x]);     // s[x] += w_f e[f,x]  (armnet.py:86-87)
-                        acc[1][x] = ffma2(bw, e2[x], acc[1][x]);
-                    }
+                    const float2 w2 = splat2(w);
+                    acc[0] = ffma2(w2, make_float2(c0.x, c0.y), acc[0]);     // s[x] += w_f e[f,x]  (armnet.py:86-87)
+                    acc[1] = ffma2(w2, make_float2(c0.z, c0.w), acc[1]);
+                    acc[2] = ffma2(w2, make_float2(c1.x, c1.y), acc[2]);
+                    acc[3] = ffma2(w2, make_float2(c1.z, c1.w), acc[3]);
+                    acc[4] = ffma2(w2, c2, acc[4]);
                 };
-                auto cross = [&](int j, float2 w0, float2 w1) {
-                    fma_field(2 * j, w0.x, w1.x);
-                    if (!ODD || j < NP - 1) fma_field(2 * j + 1, w0.y, w1.y);
+                auto cross = [&](int j, const float2 (&w)[1]) {
+                    fma_field(2 * j, w[0].x);
+                    if (!ODD || j < NP - 1) fma_field(2 * j + 1, w[0].y);
                 };
                 auto reset = [&]() {
 #pragma unroll
-                    for (int x = 0; x < EL / 2; ++x) acc[0][x] = acc[1][x] = make_float2(0.f, 0.f);
+                    for (int x = 0; x < EL / 2; ++x) acc[x] = make_float2(0.f, 0.f);
                 };
-                rows_entmax_cross<NP, ODD>(X, ep, tau, S, vrow, cross, reset);
+                rows_entmax_cross<1, NP, ODD>(X, ep, tau, S, vrow, cross, reset);
             }
             // every lane is done reading the tile: hand it back (one arrival per unit)
             __syncwarp();
@@ -454,58 +493,56 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
             if (!valid) continue;
 
             // ---- s = acc / S (entmax.py:63-64 renormalisation), z = exp(s) (armnet.py:86) [, eval-mode arm_bn, :89]
-            const int r0 = h * 256 + qd * 64 + 2 * lane;
-            float z[2][EL];
-#pragma unroll
-            for (int n = 0; n < 2; ++n) {
-                const float2 k2 = splat2(__frcp_rn(S[n]) * 1.4426950408889634f);
+            float z[EL];
+            {
+                const float2 k2 = splat2(__frcp_rn(S[0]) * 1.4426950408889634f);
 #pragma unroll
                 for (int x = 0; x < EL / 2; ++x) {
-                    const float2 t2 = fmul2(acc[n][x], k2);
-                    z[n][2 * x] = fast_ex2(t2.x);
-                    z[n][2 * x + 1] = fast_ex2(t2.y);
+                    const float2 t2 = fmul2(acc[x], k2);
+                    z[2 * x] = fast_ex2(t2.x);
+                    z[2 * x + 1] = fast_ex2(t2.y);
                 }
             }
             if (P.post_scale != nullptr) {
+                const float m = __ldg(P.post_mean + r), a = __ldg(P.post_scale + r), sh = __ldg(P.post_shift + r);
 #pragma unroll
-                for (int n = 0; n < 2; ++n) {
-                    const float m = __ldg(P.post_mean + r0 + n), a = __ldg(P.post_scale + r0 + n),
-                                sh = __ldg(P.post_shift + r0 + n);
-#pragma unroll
-                    for (int x = 0; x < EL; ++x) z[n][x] = fmaf(z[n][x] - m, a, sh);
-                }
+                for (int x = 0; x < EL; ++x) z[x] = fmaf(z[x] - m, a, sh);
             }
-            // the unit's 64 rows are contiguous in out_z: stage them, one TMA bulk store
-            float *gdst = P.out_z + ((long long)b * R + h * 256 + qd * 64) * (long long)E;
+            // the unit's 32 rows are contiguous in out_z: stage them, one TMA bulk store
+            float *gdst = P.out_z + ((long long)b * R + kb * 128 + qd * 32) * (long long)E;
             if (P.tma_store) {
-                if (lane == 0) tma_store_wait_read<0>();  // this warp's previous bulk store has drained the buffer
+                float *ost_base = ost_warp + obuf * L.out_floats;
+                obuf ^= 1;
+                if (lane == 0) tma_store_wait_read<1>();  // the bulk store before the previous one has drained this buffer
                 __syncwarp();
-                float *ost = ost_base + lane * (2 * E);
+                float *ost = ost_base + lane * E;
+                if ((E & 1) == 0) {
 #pragma unroll
-                for (int n = 0; n < 2; ++n)
+                    for (int x = 0; x < EL; x += 2)
+                        if (x < E) *reinterpret_cast<float2 *>(ost + x) = make_float2(z[x], z[x + 1]);
+                } else {
 #pragma unroll
                     for (int x = 0; x < EL; ++x)
-                        if (x < E) ost[n * E + x] = z[n][x];
+                        if (x < E) ost[x] = z[x];
+                }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_bulk(gdst, ost_base, (uint32_t)(64 * E * 4));
+                    tma_store_bulk(gdst, ost_base, (uint32_t)(32 * E * 4));
                     tma_store_commit();
                 }
             } else {
-                float *dst = gdst + lane * (2 * E);
+                float *dst = gdst + lane * E;
 #pragma unroll
-                for (int n = 0; n < 2; ++n)
-#pragma unroll
-                    for (int x = 0; x < EL; ++x)
-                        if (x < E) dst[n * E + x] = z[n][x];
+                for (int x = 0; x < EL; ++x)
+                    if (x < E) dst[x] = z[x];
             }
         }
         if (P.tma_store && lane == 0) tma_store_wait_all<0>();
     }
     tm_fence_before();
     __syncthreads();
-    if (warp == kTmConsumers) tm_dealloc(tmem, 512);
+    if (warp == kTmWarpMma) tm_dealloc(tmem, 512);
 }
 
 // One compiled shape of the kernel.

@@ -103,18 +103,28 @@ class FlatAdam:
         self.flat_g.zero_()
 
     @torch.no_grad()
-    def step(self, weight=1.0):
-        """`weight` as in GradAllReducer.step (this rank's share of the global batch times world size)."""
+    def step(self, weight=1.0, events=None):
+        """`weight` as in GradAllReducer.step (this rank's share of the global batch times world size).
+        `events`: optional list; three CUDA events (start, after the all-reduce, after clamp+Adam) are appended to it
+        (bench.py's train_c4 leg: exposed all-reduce time and bus bandwidth)."""
         from . import ops
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if events is not None else None
+        if ev:
+            ev[0].record()
         if world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+        if ev:
+            ev[1].record()
         self.t += 1
         ops.clamp_adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, weight / world, self.clamp, self.lr,
                        self.betas[0], self.betas[1], self.eps, self.t)
         # the kernel writes through raw pointers: tell torch, so every cache keyed on (data_ptr, _version) -- padded
         # embedding table, pre-contracted attention workspace, folded arm_bn, split MLP weights -- is rebuilt
         torch.autograd.graph.increment_version(self.params)
+        if ev:
+            ev[2].record()
+            events.extend(ev)
 
 
 @torch.no_grad()

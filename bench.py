@@ -46,14 +46,20 @@ WORKLOADS = {
     'c1': dict(model='armnet_1h', nfield=10, nfeat=5382, nemb=10, nhead=1, nhid=10, alpha=1.7, bsz=4096,
                mlp_nlayer=2, mlp_nhid=256),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of armnet_fwd_kernel from the committed `ncu --set full`
-# capture (profiles/r1_v6_fwd_ncu.txt): 21.82 MB read + 26.51 MB written. Below the algorithmic 92.2 MB because part
-# of the 84 MB output is still dirty in the 126 MB L2 when the kernel ends; no re-reads.
-NCU_TRAFFIC_BYTES = {('c2a', 1): 48326912}
-# FP32-pipe lane-cycles per (sample, neuron) row of armnet_fwd_kernel<39,1,10,1> from the same capture's executed-opcode
-# histogram (profiles/r1_v6_fwd_ncu.txt): FFMA2 409.5, FADD2 98, FMUL2 64 (2 pipe cycles each) + FADD 43 (+ a few FFMA / FMUL).
-# Used for the honest second ceiling: the path is FP32-issue bound, not HBM bound.
-NCU_FP32_PIPE_CYCLES_PER_ROW = {'c2a': 2 * (409.5 + 98.0 + 64.0) + 43.0 + 8.0}
+# roofline.traffic / fp32_pipe come from committed `ncu --set full` captures, keyed by (workload, kernel kind):
+# profiles/ncu_traffic.json = {"<workload>/<kind>": {"dram_bytes": dram__bytes_read.sum + dram__bytes_write.sum per launch,
+# "fp32_pipe_cycles_per_row": FMA-pipe cycles per (sample, neuron) row from the executed-opcode histogram or null,
+# "source": the extract under profiles/}}.  No entry -> null (never a number from another kernel).
+
+
+def ncu_record(workload, kind):
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            return json.load(f).get(f'{workload}/{kind}')
+    except Exception:
+        return None
+
+
 METRIC = 'CTR samples/sec (bsz=4096, Criteo-shape) at 1/2/4/8 B200; HBM GB/s vs roofline'
 
 
@@ -141,6 +147,117 @@ def trained_like_(model, seed=7):
         a.query.mul_(4.0)
 
 
+def cpu_model_string():
+    try:
+        with open('/proc/cpuinfo') as f:
+            for line in f:
+                if line.startswith('model name'):
+                    return line.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
+
+
+def reference_eager_on_gpu(w, model, batch, dev, steps=3):
+    """SURVEY.md 8d's bar: the reference's own op chain (oracle port of armnet.py:82-87: the same ATen calls) run EAGERLY
+    on the same B200 on the same batch -- what `model.cuda()` (model_utils.py:86) gives a user of the reference."""
+    import torch
+    from oracle import armnet_oracle as oracle
+    st = {k: v.detach() for k, v in model.state_dict().items()
+          if k.startswith('embedding.') or k.startswith('attn_layer.')}
+    ids, vals = batch
+
+    def run():
+        with torch.no_grad():
+            return oracle.hot_path(st, w['alpha'], ids, vals.clone())['z']
+    run()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        z = run()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    del z
+    torch.cuda.empty_cache()
+    return {'value': w['bsz'] / (ms * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms, 'steps': steps,
+            'what': 'reference op chain (embedding, 2 einsums, 50-step entmax bisection, einsum, exp) as eager torch ops '
+                    'on this GPU, same batch, hot path only (oracle port on CUDA tensors)'}
+
+
+def train_c4_leg(dev, rank, world, steps=10, warmup=3):
+    """BASELINE config 4 under the driver's eyes: one data-parallel training step of armnet at the Criteo shape with
+    nemb=16, bsz=4096 per GPU: forward + BCE loss + backward + ONE all-reduce of the flat gradient bucket + fused
+    clamp+Adam (train.py:101-114,62-65).  Device-timed, max over ranks; phases by CUDA events on rank 0."""
+    import torch
+    import torch.nn as nn
+    import torch.distributed as dist
+    import armnet_b200 as ab
+    from armnet_b200.parallel import FlatAdam
+    F, V, E, K, O, B = 39, 1000000, 16, 4, 128, 4096
+    torch.manual_seed(2025)
+    model = ab.ARMNetModel(F, V, E, K, 1.7, O, 2, 256, 0.0, False, 2, 256).to(dev).train()
+    stepper = FlatAdam(model.parameters(), lr=3e-3, clamp=1.0)
+    crit = nn.BCEWithLogitsLoss()
+    g = torch.Generator().manual_seed(100 + rank)
+    batches = [(torch.randint(0, V, (B, F), generator=g).to(dev), torch.ones(B, F, device=dev),
+                (torch.rand(B, generator=g) < 0.25).float().to(dev)) for _ in range(4)]
+    sampler = ClockSampler(dev.index or 0)
+
+    def step(i, evs):
+        ids, vals, y = batches[i % 4]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        loss = crit(model({'id': ids, 'value': vals.clone()}).reshape(-1), y)
+        e[1].record()
+        stepper.zero_grad()
+        loss.backward()
+        e[2].record()
+        opt_ev = [] if evs is not None else None
+        stepper.step(events=opt_ev)
+        if evs is not None:
+            evs.append(e + opt_ev)
+
+    for i in range(warmup):
+        step(i, None)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = []
+    t0.record()
+    for i in range(steps):
+        step(i, evs)
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    ph = [0.0] * 4
+    for e in evs:
+        ph[0] += e[0].elapsed_time(e[1])
+        ph[1] += e[1].elapsed_time(e[2])
+        ph[2] += e[3].elapsed_time(e[4])
+        ph[3] += e[4].elapsed_time(e[5])
+    ph = [x / steps for x in ph]
+    nbytes = stepper.numel() * 4
+    del model, stepper, batches
+    torch.cuda.empty_cache()
+    return {'metric': 'training samples/s (config 4: armnet nemb=16, bsz=4096/GPU, dense Adam, 1 all-reduce/step)',
+            'value': B * world * steps / (ms * 1e-3), 'unit': 'samples/s', 'n_gpus': world, 'steps': steps,
+            'ms_per_step': ms / steps, 'grad_bucket_bytes': nbytes,
+            'phase_ms': {'forward+loss': ph[0], 'backward': ph[1], 'allreduce': ph[2], 'clamp+adam': ph[3]},
+            'allreduce_bus_GBps': (2.0 * (world - 1) / world * nbytes / (ph[2] * 1e-3) / 1e9) if world > 1 else None,
+            'clocks': clocks}
+
+
 def cpu_reference_rate(w, state, steps, warmup, sample_b, full_model, seed=99):
     """The reference algorithm on the host cores: oracle port of the ATen op chain, all threads."""
     import torch
@@ -170,7 +287,10 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2a', choices=sorted(WORKLOADS))
-    ap.add_argument('--cpu-sample', type=int, default=256, help='samples per CPU-baseline step')
+    ap.add_argument('--cpu-sample', type=int, default=0,
+                    help='samples per CPU step (default: the whole batch for --impl reference, 256 for the cpu_baseline leg)')
+    ap.add_argument('--no-train-leg', action='store_true', help='skip the config-4 training-step leg (train_c4)')
+    ap.add_argument('--no-eager-leg', action='store_true', help='skip the reference-eager-on-GPU leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-flush', action='store_true', help='do not flush L2 between timed steps')
     args = ap.parse_args()
@@ -191,11 +311,12 @@ def main():
         from oracle import armnet_oracle as oracle
         st = oracle.reference_init_state(w['model'], w['nfield'], w['nfeat'], w['nemb'], w['nhead'], w['nhid'],
                                          mlp_nlayer=w['mlp_nlayer'], mlp_nhid=w['mlp_nhid'], seed=2025)
-        steps = min(args.steps, 8)
-        warm = min(args.warmup, 1)
-        rate, sec, cores = cpu_reference_rate(w, st, steps, warm, args.cpu_sample, full_model=True)
-        sample = (f'{steps} steps x {args.cpu_sample} samples of the same workload (full ARMNetModel.forward, eval), '
-                  f'torch {torch.__version__} CPU, {cores} threads')
+        sample_b = args.cpu_sample or w['bsz']                 # the arm's own config: whole batches of bsz samples
+        steps = max(3, min(args.steps, 5))                     # >= 3 timed steps; ~2-4 s each at bsz=4096 on 16 cores
+        warm = 1
+        rate, sec, cores = cpu_reference_rate(w, st, steps, warm, sample_b, full_model=True)
+        sample = (f'{steps} steps x {sample_b} samples of the same workload (full ARMNetModel.forward, eval), '
+                  f'torch {torch.__version__} CPU, {cores} threads, {sec:.2f} s/step, cpu: {cpu_model_string()}')
         print(json.dumps({
             'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'samples/s', 'n_gpus': args.gpus,
             'steps': steps, 'warmup': warm, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
@@ -338,6 +459,12 @@ def main():
                                  'unit': 'TFLOP/s', 'frac': flops / t_gemm / 1e12 / tf32_peak, 'peak_source': src},
                     'tail_kernel_us': t_tail * 1e6}
 
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_leg:
+        try:
+            eager = reference_eager_on_gpu(w, model, resident[0], dev)
+        except Exception as ex:                                  # e.g. out of memory on a shared box: report, keep going
+            eager = {'unavailable': repr(ex)[:200]}
     trained_like_(model)
     tab, ld = model._shadow.get(table) if model.padded_table else (table.detach(), table.shape[1])
     W, Q, Vv = (t.detach() for t in model._attn_weights())
@@ -360,13 +487,14 @@ def main():
     kind = ops.fused_fwd_kernel_kind(w['nfield'], w['nemb'], w['nhead'], w['nhid'], w['alpha'])
     kernel_name = {1: 'armnet_fwd_kernel', 2: 'armnet_fwd_mma_kernel (E x F products as 3xTF32 warp MMAs)',
                    3: 'armnet_fwd_tmem_kernel (attention logits by tcgen05.mma into tensor memory)'}[kind]
-    if kind == 1 and args.workload in NCU_FP32_PIPE_CYCLES_PER_ROW and clocks and clocks.get('sm_mhz'):
+    rec = ncu_record(args.workload, kind)
+    if rec and rec.get('fp32_pipe_cycles_per_row') and clocks and clocks.get('sm_mhz'):
         # warp-level FP32-pipe cycles the kernel needs per second / what 148 SMs x 4 sub-partitions offer at the sampled clock
         rows_per_s = value / n * w['nhead'] * w['nhid']
-        need = rows_per_s / 32.0 * NCU_FP32_PIPE_CYCLES_PER_ROW[args.workload]   # one warp instruction serves 32 row-threads
+        need = rows_per_s / 32.0 * rec['fp32_pipe_cycles_per_row']   # one warp instruction serves 32 row-threads
         have = 148 * 4 * clocks['sm_mhz'] * 1e6
-        fp32_pipe = {'frac': need / have, 'what': 'FMA-pipe busy fraction implied by the measured rate and the ncu '
-                     'opcode histogram (ncu direct: sm__pipe_fma_cycles_active 51.7 %)'}
+        fp32_pipe = {'frac': need / have, 'what': 'FMA-pipe busy fraction implied by the measured rate and the executed-'
+                     'opcode histogram of ' + rec.get('source', 'the committed ncu capture')}
     out = {
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': n, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
@@ -374,10 +502,11 @@ def main():
         'config': dict(cfg, l2='flushed between timed steps (256 MiB memset outside the events)'
                        if flush is not None else 'not flushed'),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': NCU_TRAFFIC_BYTES.get((args.workload, kind)), 'peak_source': peak_src,
+                     'traffic': rec.get('dram_bytes') if rec else None,
+                     'traffic_source': rec.get('source') if rec else None, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': abytes,
-                     'kernel': kernel_name + ' (attention parameters pre-contracted once per weight version by '
-                               'attn_prepare_kernel, 3.6 us, outside the per-batch step)',
+                     'kernel': kernel_name + ' (attention parameters pre-contracted once per weight version by the '
+                               'prepare kernels, ~4 us, outside the per-batch step)',
                      'note': 'path is instruction-issue/MUFU bound (entmax), not HBM bound; see DESIGN.md',
                      'fp32_pipe': fp32_pipe},
         'e2e': {'value': w['bsz'] * args.steps * n / e2e_s, 'unit': 'samples/s',
@@ -395,14 +524,24 @@ def main():
         'step_ms_min_med_max': [min(per_step), statistics.median(per_step), max(per_step)],
         'mlp': mlp_info,
         'clocks': clocks,
+        'reference_gpu_eager': eager,
     }
+    if not args.no_train_leg:
+        del scorer, model
+        torch.cuda.empty_cache()
+        try:
+            out['train_c4'] = train_c4_leg(dev, rank, world)
+        except Exception as ex:
+            out['train_c4'] = {'unavailable': repr(ex)[:300]}
     if rank == 0:
         if n == 1 and not args.no_cpu_baseline:
             st = {k: v.detach().cpu() for k, v in build_module(w).state_dict().items()}
-            rate, sec, cores = cpu_reference_rate(w, st, 3, 1, args.cpu_sample, full_model=False)
+            sample_b = args.cpu_sample or 1024
+            rate, sec, cores = cpu_reference_rate(w, st, 3, 1, sample_b, full_model=False)
             out['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-                                   'sample': f'3 steps x {args.cpu_sample} samples of the same workload (hot path '
-                                             f'only), oracle port on torch CPU, {cores} threads, {sec:.2f} s/step'}
+                                   'sample': f'3 steps x {sample_b} samples of the same workload (hot path '
+                                             f'only), oracle port on torch CPU, {cores} threads, {sec:.2f} s/step, '
+                                             f'cpu: {cpu_model_string()}'}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

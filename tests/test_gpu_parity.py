@@ -244,52 +244,94 @@ def test_bad_arguments_fail_loudly():
     t = torch.zeros(10, 10, device=d)
     with pytest.raises(RuntimeError):        # CPU tensor: no fallback
         ops.embed_gather(torch.zeros(2, 3, dtype=torch.int64), torch.ones(2, 3), torch.zeros(10, 10))
-    with pytest.raises(TypeError):           # non-contiguous values cannot be clamped in place
-        ops.embed_gather(torch.zeros(2, 3, dtype=torch.int64, device=d), torch.ones(3, 2, device=d).t(), t)
+    # a strided view of values is accepted like the reference does, and still clamped in place (armnet.py:82)
+    v_nc = (torch.ones(3, 2, device=d) * 2).t()
+    e_nc = ops.embed_gather(torch.zeros(2, 3, dtype=torch.int64, device=d), v_nc, t, clamp=(0.001, 1.0))
+    assert e_nc.shape == (2, 3, 10) and torch.equal(v_nc, torch.ones(2, 3, device=d))
+    with pytest.raises(TypeError):           # integer values are not
+        ops.embed_gather(torch.zeros(2, 3, dtype=torch.int64, device=d), torch.ones(2, 3, device=d).long(), t)
     with pytest.raises(RuntimeError):        # alpha < 1 -> ARMNET_ERR_SHAPE
         ops.entmax_forward(torch.zeros(4, 8, device=d), 0.5)
     with pytest.raises(RuntimeError):        # 65 fields -> ARMNET_ERR_UNSUPPORTED
         ops.entmax_forward(torch.zeros(4, 65, device=d), 1.5)
 
 
-@pytest.mark.parametrize('regime', ['init', 'trained'])
-def test_full_size_criteo_batch_properties(regime):
-    """BASELINE config 2 at full size (B=4096, 39 fields, 1M vocab, nemb 10, 4 heads x 128 neurons):
-    oracle on a sample of rows, plus size-independent properties on the whole batch."""
+def _full_size_case(F, E, K, O, V, B, alpha, regime, tuning, expect_kind, ld_pad=None, n_pick=48):
+    """One BASELINE configuration at its full size: the oracle on a sample of rows spread over the batch, plus
+    size-independent properties on the whole batch -- finite / positive output, in-place clamp, permutation equivariance
+    over samples, determinism, and independence of the table's row pitch (the TMA-gather path)."""
     from armnet_b200 import ops
     from oracle import armnet_oracle as oracle
     d = dev()
-    st = _criteo_state(nfeat=1000000)
+    st = oracle.reference_init_state('armnet', F, V, E, K, O, mlp_nhid=32, seed=2025)
+    st = {k: v for k, v in st.items() if k.startswith('embedding.') or k.startswith('attn_layer.')}
     gen = torch.Generator().manual_seed(11)
     if regime == 'trained':
         st['embedding.embedding.weight'].normal_(0, 1.0, generator=gen)
         st['attn_layer.bilinear_w'] *= 4
         st['attn_layer.query'] *= 4
-    B = 4096
-    ids = torch.randint(0, 1000000, (B, 39), generator=gen)
-    vals = torch.rand(B, 39, generator=gen) * 1.2
+    ids = torch.randint(0, V, (B, F), generator=gen)
+    ids[0, 0], ids[-1, -1] = V - 1, V - 1                       # the last table row (byte offsets beyond 2^31 at C3)
+    vals = torch.rand(B, F, generator=gen) * 1.2
     W, Q, Vv = (st[k].to(d) for k in ('attn_layer.bilinear_w', 'attn_layer.query', 'attn_layer.values'))
     table = st['embedding.embedding.weight'].to(d)
-    v_d = vals.clone().to(d)
-    z, ex = ops.fused_forward(ids.to(d), v_d, table, W, Q, Vv, 1.7, want_tau=True)
-    assert torch.isfinite(z).all() and (z > 0).all()
-    assert torch.equal(v_d.cpu(), vals.clamp(0.001, 1.0))
-    # oracle on 48 samples spread over the batch
-    pick = torch.arange(0, B, B // 48)[:48]
-    ref = oracle.hot_path(st, 1.7, ids[pick], vals[pick].clone())
-    assert norm_rel(z[pick.to(d)].cpu(), ref['z']) <= TOL_NORM
-    # permutation equivariance over samples (each row only depends on its own sample)
-    perm = torch.randperm(B, generator=gen)
-    z2, _ = ops.fused_forward(ids[perm].to(d), vals[perm].clone().to(d), table, W, Q, Vv, 1.7)
-    assert norm_rel(z2.cpu(), z[perm.to(d)].cpu()) <= 2e-6
-    # determinism
-    z3, _ = ops.fused_forward(ids.to(d), vals.clone().to(d), table, W, Q, Vv, 1.7)
-    assert torch.equal(z3, z)
-    # the padded (TMA-gather) table gives the same bits as the 40-byte-row table
-    tp = torch.zeros(table.shape[0], 12, device=d)
-    tp[:, :10] = table
-    z4, _ = ops.fused_forward(ids.to(d), vals.clone().to(d), tp, W, Q, Vv, 1.7, ld=12, nemb=10)
-    assert torch.equal(z4, z)
+    ld = E if ld_pad is None else ld_pad
+    if ld != E:
+        tab = torch.zeros(V, ld, device=d)
+        tab[:, :E] = table
+    else:
+        tab = table
+    with ops.tuning(**tuning):
+        assert ops.fused_fwd_kernel_kind(F, E, K, O, alpha) == expect_kind
+        v_d = vals.clone().to(d)
+        z, _ = ops.fused_forward(ids.to(d), v_d, tab, W, Q, Vv, alpha, ld=ld, nemb=E)
+        assert z.shape == (B, K * O, E)
+        assert torch.isfinite(z).all() and (z > 0).all()
+        assert torch.equal(v_d.cpu(), vals.clamp(0.001, 1.0))
+        # oracle on samples spread over the batch (first and last included)
+        pick = torch.cat([torch.arange(0, B, max(B // n_pick, 1))[:n_pick], torch.tensor([B - 1])])
+        ref = oracle.hot_path(st, alpha, ids[pick], vals[pick].clone())
+        assert norm_rel(z[pick.to(d)].cpu(), ref['z']) <= TOL_NORM
+        # permutation equivariance over samples (each row only depends on its own sample; tile / warp neighbours change)
+        perm = torch.randperm(B, generator=gen)
+        z2, _ = ops.fused_forward(ids[perm].to(d), vals[perm].clone().to(d), tab, W, Q, Vv, alpha, ld=ld, nemb=E)
+        assert norm_rel(z2.cpu(), z[perm.to(d)].cpu()) <= 2e-6
+        # determinism
+        z3, _ = ops.fused_forward(ids.to(d), vals.clone().to(d), tab, W, Q, Vv, alpha, ld=ld, nemb=E)
+        assert torch.equal(z3, z)
+    return z, ids, vals, table, (W, Q, Vv)
+
+
+@pytest.mark.parametrize('regime', ['init', 'trained'])
+@pytest.mark.parametrize('kernel', ['fp32', 'tmem'])
+def test_full_size_criteo_batch_properties(regime, kernel):
+    """BASELINE config 2 at full size (B=4096, 39 fields, 1M vocab, nemb 10, 4 heads x 128 neurons), through
+    armnet_fwd_kernel and through armnet_fwd_tmem_kernel (the default on the 16-byte-pitch table the module keeps)."""
+    from armnet_b200 import ops
+    d = dev()
+    tuning = dict(tmem=0, mma=0) if kernel == 'fp32' else dict(tmem=1)
+    z, ids, vals, table, (W, Q, Vv) = _full_size_case(39, 10, 4, 128, 1000000, 4096, 1.7, regime, tuning,
+                                                      1 if kernel == 'fp32' else 3, ld_pad=12)
+    # the 40-byte-row table (no TMA gather; always armnet_fwd_kernel) gives the same function
+    with ops.tuning(**tuning):
+        z4, _ = ops.fused_forward(ids.to(d), vals.clone().to(d), table, W, Q, Vv, 1.7)
+    if kernel == 'fp32':
+        assert torch.equal(z4, z)                       # same kernel, same bits whatever the gather path
+    else:
+        assert norm_rel(z4.cpu(), z.cpu()) <= 2e-6      # two kernels, one function
+
+
+def test_full_size_avazu_shape_c3():
+    """BASELINE config 3 at full size: 22 fields, 1.5M vocab, nemb 100 (rows split over 4 lanes), h 32, alpha 1.5,
+    B=8192; the 600 MB table puts row offsets beyond 2^31 bytes."""
+    _full_size_case(22, 100, 1, 32, 1500000, 8192, 1.5, 'trained', dict(tmem=-1, mma=-1), 1, n_pick=32)
+
+
+@pytest.mark.parametrize('regime', ['init', 'trained'])
+def test_full_size_config4_shape_nemb16(regime):
+    """BASELINE config 4's forward at full size: Criteo shape with nemb 16, K*O = 512, B=4096 -- the default-on
+    armnet_fwd_mma_kernel instance (the two E x F products as 3xTF32 warp MMAs)."""
+    _full_size_case(39, 16, 4, 128, 1000000, 4096, 1.7, regime, dict(tmem=-1, mma=-1), 2)
 
 
 @pytest.mark.parametrize('alpha', [1.0, 1.3, 1.5, 1.7, 2.0])

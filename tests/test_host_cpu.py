@@ -28,8 +28,8 @@ def test_argument_validation_without_gpu():
     from armnet_b200 import _capi
     lib = _capi.lib
     # row-pair tables with odd strides, then the tensor-memory kernel's operands: 512 packed M' rows of 128 bytes and
-    # 256 field-packed value row pairs of 42 float2
-    assert lib.armnet_fused_workspace_bytes(39, 10, 4, 128) == 256 * (11 + 39) * 2 * 4 + 512 * 128 + 256 * 42 * 8
+    # 512 field-packed value rows of 22 float2
+    assert lib.armnet_fused_workspace_bytes(39, 10, 4, 128) == 256 * (11 + 39) * 2 * 4 + 512 * 128 + 512 * 22 * 8
     assert lib.armnet_fused_workspace_bytes(39, 10, 4, 100) == 200 * (11 + 39) * 2 * 4     # no tensor-memory instance
     assert lib.armnet_fused_workspace_bytes(39, 100, 1, 32) > 0
     assert lib.armnet_fused_workspace_bytes(65, 10, 4, 128) == 0        # > 64 fields: no instance

@@ -99,6 +99,8 @@ def load_data(args):
     files = []
     for pat in ('tr*libsvm', 'va*libsvm', 'te*libsvm'):           # data_loader.py:58-61
         hits = sorted(glob.glob(os.path.join(d, pat)))
+        if not hits:    # only the binary cache was shipped (tools/make_frappe_cache.py): <name>.libsvm.armnet_bin/
+            hits = [h[:-len('.armnet_bin')] for h in sorted(glob.glob(os.path.join(d, pat + '.armnet_bin')))]
         if not hits:
             raise FileNotFoundError(f'no {pat} under {d}')
         files.append(hits[0])
