@@ -37,6 +37,7 @@ Tuning &tuning() {
     static Tuning t = [] {
         Tuning x;
         x.tmem = env_int("ARMNET_TMEM", -1);
+        x.tmem_rows = env_int("ARMNET_TMEM_ROWS", -1);
         x.mma = env_int("ARMNET_MMA", -1);
         const char *sp = getenv("ARMNET_MMA_SPLIT");
         x.mma_split_rna = (sp && sp[0] == 'r') ? 1 : 0;
@@ -128,7 +129,7 @@ int armnet_set_tuning(const char *key, int value) {
     if (key == nullptr) return ARMNET_ERR_NULL;
     armnet::Tuning &t = armnet::tuning();
     struct { const char *name; int *field; } tab[] = {
-        {"tmem", &t.tmem}, {"mma", &t.mma}, {"mma_split_rna", &t.mma_split_rna}, {"mma_warps", &t.mma_warps},
+        {"tmem", &t.tmem}, {"tmem_rows", &t.tmem_rows}, {"mma", &t.mma}, {"mma_split_rna", &t.mma_split_rna}, {"mma_warps", &t.mma_warps},
         {"force_nw", &t.force_nw}, {"force_look", &t.force_look}, {"lockstep", &t.lockstep},
         {"no_tma_gather", &t.no_tma_gather}, {"no_tma_store", &t.no_tma_store}, {"gemm_1cta", &t.gemm_1cta}};
     for (auto &e : tab) {

@@ -19,8 +19,20 @@ static const TmemInstance *select_tmem_instance(int F) {
 
 bool tmem_shape_supported(int F, int E, int R) {
     // tensor memory: A operand (R/128 blocks x 32 columns) + 4 D slots of 2 samples x 2 NP fields
-    return select_tmem_instance(F) != nullptr && E >= 1 && E <= kTmEL && R % 128 == 0 && R >= 128 &&
-           (R / 128) * kTmKP + 4 * 4 * select_tmem_instance(F)->NP <= 512;
+    const TmemInstance *I = select_tmem_instance(F);
+    if (I == nullptr || E < 1 || E > kTmEL || R % 128 != 0 || R < 128 || (R / 128) * kTmKP + 4 * 4 * I->NP > 512)
+        return false;
+    // shared memory (sm_100: 227 KB opt-in per CTA) with the shallowest gather ring
+    TmemParams P;
+    memset(&P, 0, sizeof(P));
+    P.F = F;
+    P.E = E;
+    P.R = R;
+    P.row_bytes = (E * 4 + 15) / 16 * 16;
+    P.tma_store = 1;
+    P.look = 1;
+    P.n_raw = 2;
+    return TmemSmem(I->NP, 2, P).total <= 232448;
 }
 
 // Workspace of the TMEM kernel: Apk floats [R/128][128][32], then Vpk float2 [R][vstr] (16-byte padded).
@@ -133,23 +145,27 @@ int tmem_launch(const char *who, const void *ids, int ids_i32, float *values, co
     P.n_tiles = (int)((B + 1) / 2);
     P.row_bytes = (E * 4 + 15) / 16 * 16;
     P.tma_store = ((uintptr_t)out_z % 16 == 0) ? 1 : 0;
+    // rows per thread: 2 (logits streamed from tensor memory) when K*O % 256 == 0, unless tuning "tmem_rows" == 1 asks
+    // for the one-row mapping (logits in registers)
+    const int NR = (R % 256 == 0 && tuning().tmem_rows != 1) ? 2 : 1;
     // gather look-ahead: as deep as the raw ring that fits (<= 16 tiles = 32 samples: the mbarrier block holds 32)
     int look = 16;
     for (; look >= 1; --look) {
         P.look = look;
         P.n_raw = 2 * look;
-        const TmemSmem L(I->NP, P);
+        const TmemSmem L(I->NP, NR, P);
         if (L.total <= di.smem_optin) break;
     }
     if (look < 1) {
         set_error("%s: F=%d E=%d K*O=%d does not fit the shared memory of the tensor-memory kernel", who, F, E, R);
         return ARMNET_ERR_UNSUPPORTED;
     }
-    const TmemSmem L(I->NP, P);
+    const TmemSmem L(I->NP, NR, P);
+    const void *kernel = NR == 2 ? I->kernel2 : I->kernel;
     const unsigned grid = (unsigned)(P.n_tiles < di.sm_count ? P.n_tiles : di.sm_count);
-    ARMNET_CUDA_TRY(cudaFuncSetAttribute(I->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
+    ARMNET_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
     void *args[] = {(void *)&P};
-    ARMNET_CUDA_TRY(cudaLaunchKernel(I->kernel, dim3(grid), dim3(kTmThreads), args, (size_t)L.total, st));
+    ARMNET_CUDA_TRY(cudaLaunchKernel(kernel, dim3(grid), dim3(kTmThreads), args, (size_t)L.total, st));
     return ARMNET_OK;
 }
 

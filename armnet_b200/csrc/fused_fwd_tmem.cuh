@@ -33,6 +33,7 @@
 #pragma once
 
 #include "entmax_rows.cuh"
+#include "entmax_stream.cuh"
 #include "fused_fwd.cuh"
 
 namespace armnet {
@@ -82,21 +83,21 @@ struct TmemSmem {
     int off_bar, off_tiles, off_V, off_raw, off_vals, off_out, total;
     int tile_bytes, v_bytes, vstr, raw_sample_bytes, fpad, out_floats;
     __host__ __device__ static int up(int x, int a) { return (x + a - 1) / a * a; }
-    __host__ __device__ TmemSmem(int NP, const TmemParams &P) {
+    __host__ __device__ TmemSmem(int NP, int NR, const TmemParams &P) {
         const int NFP = 2 * NP;
         fpad = NFP;
         vstr = NP + 2;                     // float2 per row; (NP + 2) * 8 bytes = 16 * odd for NP = 20: conflict-free LDS.128
         tile_bytes = 2 * NFP * kTmKP * 4;  // 2 samples x NFP rows x 128 bytes (a multiple of 1024 when NFP % 8 == 0)
         v_bytes = up(P.R * vstr * 8, 16);
         raw_sample_bytes = up(P.F * P.row_bytes, 16);
-        out_floats = 32 * P.E;
+        out_floats = 64 * P.E;             // per warp: two pieces of 32 rows (NR = 2: one unit; NR = 1: two units in flight)
         off_bar = 0;                       // mbarriers + counters: 1024 bytes
         off_tiles = 1024;
         off_V = off_tiles + kTmTiles * tile_bytes;
         off_raw = up(off_V + v_bytes, 128);
         off_vals = up(off_raw + P.n_raw * raw_sample_bytes, 16);
         off_out = up(off_vals + P.n_raw * fpad * 4, 128);
-        total = off_out + (P.tma_store ? kTmConsumers * 2 * out_floats * 4 : 0);   // two staging buffers per warp
+        total = off_out + (P.tma_store ? kTmConsumers * out_floats * 4 : 0);
     }
 };
 
@@ -175,17 +176,21 @@ __device__ __forceinline__ void tm_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // NP field pairs per row: F = 2 NP (ODD = false) or 2 NP - 1 (ODD = true).  NFP = 2 NP rows per sample in the B tile.
-template <int NP, bool ODD>
+// NR = 1: a thread owns one row, its logits in registers (4 D slots of one A block, freed as soon as they are loaded).
+// NR = 2: a thread owns two rows (same TMEM lane of two A blocks) whose logits are streamed from tensor memory on every
+//         pass (entmax_stream.cuh): every shared-memory read of an embedding row feeds two rows -- the one-row mapping is
+//         bound by the shared-memory -> register return path -- and a D slot (2 blocks) lives until its units are done.
+template <int NP, bool ODD, int NR>
 __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __grid_constant__ TmemParams P) {
     constexpr int NFP = 2 * NP;
     static_assert(NFP % 8 == 0 && 2 * NFP <= 256 && (2 * NFP) % 16 == 0, "two samples of NFP rows are the N of one MMA");
     static_assert(NP % 4 == 0 && (NP < 16 || NP >= 16), "tcgen05.ld shapes: one .x32 for 16 pairs, .x8 for every 4 more");
-    constexpr int DSLOT = 2 * NFP;  // TMEM columns of a D slot: one A block (128 neurons) x 2 samples x NFP fields
-    constexpr int NSLOT = 4;        // D slots (A operand: <= 192 columns, 4 x 80 = 320)
+    constexpr int DSLOT = NR * 2 * NFP;  // TMEM columns of a D slot: NR A blocks (128 neurons each) x 2 samples x NFP fields
+    constexpr int NSLOT = 4 / NR;        // D slots (A operand: <= 192 columns, D: 320)
     constexpr int EL = kTmEL;
     extern __shared__ __align__(1024) unsigned char smem_tm[];
     unsigned char *smem = smem_tm;
-    const TmemSmem L(NP, P);
+    const TmemSmem L(NP, NR, P);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
     uint64_t *bar_par = bar;                        // V table landed
     uint64_t *d_full = bar + 1;                     // [4]  MMAs of an item done (tcgen05.commit)
@@ -205,7 +210,8 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = P.F, E = P.E, R = P.R;
-    const int NBLK = R >> 7;         // A blocks of 128 neurons = items per tile
+    const int NBLK = R >> 7;         // A blocks of 128 neurons
+    const int IPT = NBLK / NR;       // items per tile (an item = NR blocks x 2 samples)
     const int A_COLS = NBLK * kTmKP;
     const int G = (int)gridDim.x;
     const int n_local = (P.n_tiles - (int)blockIdx.x + G - 1) / G;   // tiles blockIdx.x + t * G
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
         }
         for (int s = 0; s < kTmTiles; ++s) {
             mbar_init(&tile_full[s], 1);
-            mbar_init(&tile_empty[s], NBLK * 8);
+            mbar_init(&tile_empty[s], IPT * 8);
         }
         for (int s = 0; s < P.n_raw; ++s) {
             mbar_init(&raw_full[s], 1);
@@ -397,16 +403,18 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
             const int bt = t % kTmTiles;
             tm_wait(&tile_full[bt], (uint32_t)(t / kTmTiles) & 1u);
             const uint64_t db = tm_desc_sw128(tiles + bt * L.tile_bytes);
-            for (int kb = 0; kb < NBLK; ++kb) {
-                const int i = t * NBLK + kb, slot = i % NSLOT;
+            for (int h = 0; h < IPT; ++h) {
+                const int i = t * IPT + h, slot = i % NSLOT;
                 if (i >= NSLOT) tm_wait(&d_empty[slot], (uint32_t)(i / NSLOT - 1) & 1u);
                 tm_fence_after();
                 if (lane == 0) {
                     const uint32_t d = d_base + (uint32_t)(slot * DSLOT);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tm_mma_tf32_ts(d, tmem + (uint32_t)(kb * kTmKP + k * 8), db + (uint64_t)(k * 32 >> 4), idesc,
-                                       (uint32_t)k);
+                    for (int j = 0; j < NR; ++j)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tm_mma_tf32_ts(d + (uint32_t)(j * 2 * NFP), tmem + (uint32_t)((h * NR + j) * kTmKP + k * 8),
+                                           db + (uint64_t)(k * 32 >> 4), idesc, (uint32_t)k);
                     tm_commit(&d_full[slot]);
                 }
                 __syncwarp();
@@ -417,12 +425,129 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
     } else {
         // =========================================================== consumer warps
         const int qd = warp & 3;
-        const int n_units = n_local * NBLK * 2;
-        float *ost_warp = outs + warp * 2 * L.out_floats;
+        const int n_units = n_local * IPT * 2;
+        float *ost_warp = outs + warp * L.out_floats;
         int obuf = 0;
         tm_wait(bar_par, 0);
         int u_next = 0;
         if (lane == 0) u_next = atomicAdd(&next_unit[qd], 1);
+        if constexpr (NR == 2) {
+        for (;;) {
+            const int u = __shfl_sync(0xffffffffu, u_next, 0);
+            if (u >= n_units) break;
+            const int i = u >> 1, s = u & 1;       // item, sample inside the tile
+            const int t = i / IPT, h = i - t * IPT;
+            const int slot = i % NSLOT;
+            const int bt = t % kTmTiles;
+            const long long b = 2 * ((long long)blockIdx.x + (long long)t * G) + s;
+            const bool valid = b < P.B;
+            const int r0 = h * 256 + qd * 32 + lane;   // this lane's two neurons: r0 and r0 + 128
+            tm_wait(&d_full[slot], (uint32_t)(i / NSLOT) & 1u);
+            tm_fence_after();
+            if (lane == 0) u_next = atomicAdd(&next_unit[qd], 1);   // claim the next unit: the latency hides under this one
+            tm_wait(&tile_full[bt], (uint32_t)(t / kTmTiles) & 1u);
+
+            float2 acc[2][EL / 2];
+            float tau[2], S[2] = {1.f, 1.f};
+            if (valid) {
+                const uint32_t t0 = d_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(slot * DSLOT + s * NFP);
+                const unsigned char *eb = tiles + bt * L.tile_bytes + s * (NFP * 128);
+                const float4 *vr0 = reinterpret_cast<const float4 *>(Vs + (size_t)r0 * L.vstr);
+                const float4 *vr1 = reinterpret_cast<const float4 *>(Vs + (size_t)(r0 + 128) * L.vstr);
+                auto vrow = [&](int n, int j) -> float2 {
+                    const float4 v4 = (n ? vr1 : vr0)[j >> 1];
+                    return (j & 1) ? make_float2(v4.z, v4.w) : make_float2(v4.x, v4.y);
+                };
+                auto fma_field = [&](int f, float w0, float w1) {
+                    const unsigned char *row = eb + f * 128;
+                    const int sw = f & 7;
+                    const float4 c0 = *reinterpret_cast<const float4 *>(row + ((0 ^ sw) << 4));
+                    const float4 c1 = *reinterpret_cast<const float4 *>(row + ((1 ^ sw) << 4));
+                    const float2 c2 = *reinterpret_cast<const float2 *>(row + ((2 ^ sw) << 4));
+                    const float2 e2[EL / 2] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y),
+                                               make_float2(c1.z, c1.w), c2};
+                    const float2 a = splat2(w0), bw = splat2(w1);
+#pragma unroll
+                    for (int x = 0; x < EL / 2; ++x) {
+                        acc[0][x] = ffma2(a, e2[x], acc[0][x]);     // s[x] += w_f e[f,x]  (armnet.py:86-87)
+                        acc[1][x] = ffma2(bw, e2[x], acc[1][x]);
+                    }
+                };
+                auto cross = [&](int j, float2 w0, float2 w1) {
+                    fma_field(2 * j, w0.x, w1.x);
+                    if (!ODD || j < NP - 1) fma_field(2 * j + 1, w0.y, w1.y);
+                };
+                auto reset = [&]() {
+#pragma unroll
+                    for (int x = 0; x < EL / 2; ++x) acc[0][x] = acc[1][x] = make_float2(0.f, 0.f);
+                };
+                float2 X[2][NP];   // phase-1 copy of the logits (entmax_stream.cuh); the cross passes re-stream them
+#pragma unroll
+                for (int n = 0; n < 2; ++n) {
+                    const uint32_t tn = t0 + (uint32_t)(n * 2 * NFP);
+                    if (NP >= 16) tm_ld32(tn, &X[n][0]);
+#pragma unroll
+                    for (int j = (NP >= 16 ? 16 : 0); j < NP; j += 4) tm_ld8(tn + 2 * j, &X[n][j]);
+                }
+                tm_ld_wait();
+                if (ODD) X[0][NP - 1].y = X[1][NP - 1].y = neg_inf();
+                stream_entmax_cross<NP, ODD>(X, t0, t0 + 2 * NFP, ep, tau, S, vrow, cross, reset);
+            }
+            // logits and e rows are not read any more: hand the D slot and the tile back (one arrival per unit each)
+            tm_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&d_empty[slot]);
+                mbar_arrive(&tile_empty[bt]);
+            }
+            if (!valid) continue;
+
+            // ---- s = acc / S (entmax.py:63-64 renormalisation), z = exp(s) (armnet.py:86) [, eval-mode arm_bn, :89]
+            float *ost_base = ost_warp;
+            if (P.tma_store) {
+                if (lane == 0) tma_store_wait_read<0>();  // the previous unit's bulk stores (a whole unit ago) have drained
+                __syncwarp();
+            }
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                const int r = r0 + n * 128;
+                float z[EL];
+                const float2 k2 = splat2(__frcp_rn(S[n]) * 1.4426950408889634f);
+#pragma unroll
+                for (int x = 0; x < EL / 2; ++x) {
+                    const float2 t2 = fmul2(acc[n][x], k2);
+                    z[2 * x] = fast_ex2(t2.x);
+                    z[2 * x + 1] = fast_ex2(t2.y);
+                }
+                if (P.post_scale != nullptr) {
+                    const float m = __ldg(P.post_mean + r), a = __ldg(P.post_scale + r), sh = __ldg(P.post_shift + r);
+#pragma unroll
+                    for (int x = 0; x < EL; ++x) z[x] = fmaf(z[x] - m, a, sh);
+                }
+                float *dst = P.tma_store ? ost_base + n * 32 * E + lane * E
+                                         : P.out_z + ((long long)b * R + r) * (long long)E;
+                if ((E & 1) == 0 && P.tma_store) {
+#pragma unroll
+                    for (int x = 0; x < EL; x += 2)
+                        if (x < E) *reinterpret_cast<float2 *>(dst + x) = make_float2(z[x], z[x + 1]);
+                } else {
+#pragma unroll
+                    for (int x = 0; x < EL; ++x)
+                        if (x < E) dst[x] = z[x];
+                }
+            }
+            if (P.tma_store) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {   // two pieces of 32 consecutive rows (neurons 256h + 32qd .. and + 128)
+                    float *g0 = P.out_z + ((long long)b * R + h * 256 + qd * 32) * (long long)E;
+                    tma_store_bulk(g0, ost_base, (uint32_t)(32 * E * 4));
+                    tma_store_bulk(g0 + 128 * E, ost_base + 32 * E, (uint32_t)(32 * E * 4));
+                    tma_store_commit();
+                }
+            }
+        }
+        } else {
         for (;;) {
             const int u = __shfl_sync(0xffffffffu, u_next, 0);
             if (u >= n_units) break;
@@ -511,7 +636,7 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
             // the unit's 32 rows are contiguous in out_z: stage them, one TMA bulk store
             float *gdst = P.out_z + ((long long)b * R + kb * 128 + qd * 32) * (long long)E;
             if (P.tma_store) {
-                float *ost_base = ost_warp + obuf * L.out_floats;
+                float *ost_base = ost_warp + obuf * (L.out_floats / 2);
                 obuf ^= 1;
                 if (lane == 0) tma_store_wait_read<1>();  // the bulk store before the previous one has drained this buffer
                 __syncwarp();
@@ -538,6 +663,7 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
                     if (x < E) dst[x] = z[x];
             }
         }
+        }
         if (P.tma_store && lane == 0) tma_store_wait_all<0>();
     }
     tm_fence_before();
@@ -549,8 +675,11 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
 struct TmemInstance {
     int NP;
     int odd;
-    const void *kernel;
+    const void *kernel;    // one row per thread, logits in registers
+    const void *kernel2;   // two rows per thread, logits streamed from tensor memory (needs K*O % 256 == 0)
 };
-#define ARMNET_TMEM_INSTANCE(NP, ODD) { NP, ODD, (const void *)&armnet_fwd_tmem_kernel<NP, (ODD) != 0> }
+#define ARMNET_TMEM_INSTANCE(NP, ODD)                                               \
+    { NP, ODD, (const void *)&armnet_fwd_tmem_kernel<NP, (ODD) != 0, 1>,            \
+      (const void *)&armnet_fwd_tmem_kernel<NP, (ODD) != 0, 2> }
 
 }  // namespace armnet

@@ -237,7 +237,7 @@ def set_tuning(key, value):
 
 class tuning:
     """with ops.tuning(tmem=0, mma=1): ...  -- switches restored to the library defaults (-1 / 0) on exit."""
-    _DEFAULTS = {'tmem': -1, 'mma': -1, 'mma_warps': -1, 'force_nw': -1, 'force_look': -1}
+    _DEFAULTS = {'tmem': -1, 'tmem_rows': -1, 'mma': -1, 'mma_warps': -1, 'force_nw': -1, 'force_look': -1}
 
     def __init__(self, **kw):
         self.kw = kw

@@ -241,7 +241,7 @@ int armnet_libsvm_parse(const char *path, int nfield, int64_t capacity, int32_t 
 int armnet_last_launch_count(void);
 
 /* Tuning / experiment switches (process-global; defaults come from the ARMNET_* environment variables, which are read
- * ONCE, at the first use, never in a launch path).  Keys: "tmem", "mma", "mma_split_rna", "mma_warps", "force_nw",
+ * ONCE, at the first use, never in a launch path).  Keys: "tmem", "tmem_rows", "mma", "mma_split_rna", "mma_warps", "force_nw",
  * "force_look", "lockstep", "no_tma_gather", "no_tma_store", "gemm_1cta".  value -1 = library default.
  * Returns ARMNET_ERR_UNSUPPORTED for an unknown key.  Not part of the reference's surface: tests and A/B runs only. */
 int armnet_set_tuning(const char *key, int value);

@@ -441,6 +441,7 @@ TMEM_CASES = [
     (1.7, 40, 10, 2, 128, 1.0, 40),      # even field count, one item per tile
     (1.9, 39, 10, 6, 128, 2.0, 9),       # three items per tile (K*O = 768: the tensor-memory limit)
     (1.3, 39, 10, 4, 64, 1.0, 21),       # q > 2: no Hoelder bound, bound-started q-norm Newton
+    (1.7, 39, 10, 3, 128, 1.0, 19),      # K*O = 384: not a multiple of 256 -> one row per thread only
     (1.5, 39, 10, 4, 64, 1.0, 21),       # alpha = 1.5: square mode, no MUFU
     (2.0, 39, 10, 4, 64, 2.0, 21),       # C2b: sparsemax (Michelot)
     (1.0, 40, 10, 2, 128, 1.0, 21),      # softmax
@@ -474,31 +475,38 @@ def test_tensor_memory_kernel_matches_oracle(alpha, F, E, K, O, scale, B):
     tab = torch.zeros(V, ld, device=d)
     tab[:, :E] = table.to(d)
     out = {}
-    for kind, tm in (('tmem', 1), ('fp32', 0)):
-        with ops.tuning(tmem=tm, mma=0):
+    # both thread mappings of the kernel: one row per thread (logits in registers) and two rows per thread (logits
+    # streamed from tensor memory; needs K*O % 256 == 0, the default there), and armnet_fwd_kernel
+    kinds = [('tmem1', dict(tmem=1, tmem_rows=1, mma=0)), ('fp32', dict(tmem=0, mma=0))]
+    if R % 256 == 0:
+        kinds.insert(0, ('tmem2', dict(tmem=1, tmem_rows=2, mma=0)))
+    for kind, tune in kinds:
+        with ops.tuning(**tune):
             vals = values.clone().to(d)
-            z, _ = ops.fused_forward(ids.to(d).int() if kind == 'tmem' else ids.to(d), vals, tab, W.to(d), Q.to(d), Vv.to(d),
-                                     alpha, ld=ld, nemb=E)
+            z, _ = ops.fused_forward(ids.to(d).int() if kind == 'tmem1' else ids.to(d), vals, tab, W.to(d), Q.to(d),
+                                     Vv.to(d), alpha, ld=ld, nemb=E)
             torch.cuda.synchronize()
             assert torch.equal(vals.cpu(), values.clamp(0.001, 1.0))
             out[kind] = z.cpu()
-    assert out['tmem'].shape == (B, R, E)
     z64 = ref64['z'].reshape(B, R, E)
-    fin = torch.isfinite(z64) & (z64.abs() < 1e30)
-    assert torch.equal(torch.isfinite(out['tmem']) & (out['tmem'].abs() < 1e30), fin)
-    if 'z' in own and fin.all():
-        bound = max(TOL_NORM * z64.abs().max().item(), 2.0 * own['z'])
-        err = (out['tmem'].double() - z64).abs().max().item()
-        assert err <= bound, (err, bound, own['z'])
-    # log domain (s = log z): the tolerance north_star states for the interaction logits, element by element where the
-    # reference itself is that accurate
     s64 = ref64['s'].reshape(B, R, E)
-    s_err = (torch.log(out['tmem'].double().clamp_min(1e-300)) - s64).abs()[fin].max().item()
-    assert s_err <= max(TOL_NORM * s64.abs().max().item(), 2.0 * own['s']) + 3e-7 * s64.abs().max().item(), s_err
-    # the two kernels agree far inside the tolerance
+    fin = torch.isfinite(z64) & (z64.abs() < 1e30)
     zf = out['fp32']
-    assert ((out['tmem'] - zf)[fin].abs() <= 2e-5 * zf[fin].abs().clamp_min(1e-30) *
-            max(1.0, ref['s'].abs().max().item())).all()
+    for kind in [k for k, _ in kinds if k != 'fp32']:
+        zt = out[kind]
+        assert zt.shape == (B, R, E)
+        assert torch.equal(torch.isfinite(zt) & (zt.abs() < 1e30), fin), kind
+        if 'z' in own and fin.all():
+            bound = max(TOL_NORM * z64.abs().max().item(), 2.0 * own['z'])
+            err = (zt.double() - z64).abs().max().item()
+            assert err <= bound, (kind, err, bound, own['z'])
+        # log domain (s = log z): the tolerance north_star states for the interaction logits, element by element where
+        # the reference itself is that accurate
+        s_err = (torch.log(zt.double().clamp_min(1e-300)) - s64).abs()[fin].max().item()
+        assert s_err <= max(TOL_NORM * s64.abs().max().item(), 2.0 * own['s']) + 3e-7 * s64.abs().max().item(), (kind, s_err)
+        # the kernels agree far inside the tolerance
+        assert ((zt - zf)[fin].abs() <= 2e-5 * zf[fin].abs().clamp_min(1e-30) *
+                max(1.0, ref['s'].abs().max().item())).all(), kind
 
 
 def test_tensor_memory_kernel_long_batch_ring_wraparound():
@@ -518,6 +526,8 @@ def test_tensor_memory_kernel_long_batch_ring_wraparound():
     tab = torch.zeros(V, 12, device=d)
     tab[:, :E] = table.to(d)
     post = (torch.randn(R, device=d) * 0.1 + 1, torch.rand(R, device=d) + 0.5, torch.randn(R, device=d))
+    with ops.tuning(tmem=1, tmem_rows=1):
+        z1r, _ = ops.fused_forward(ids.to(d), values.clone().to(d), tab, W.to(d), Q.to(d), Vv.to(d), alpha, ld=12, nemb=E)
     with ops.tuning(tmem=1):
         z1, _ = ops.fused_forward(ids.to(d), values.clone().to(d), tab, W.to(d), Q.to(d), Vv.to(d), alpha, ld=12, nemb=E)
         z2, _ = ops.fused_forward(ids.to(d), values.clone().to(d), tab, W.to(d), Q.to(d), Vv.to(d), alpha, ld=12, nemb=E)
@@ -527,6 +537,7 @@ def test_tensor_memory_kernel_long_batch_ring_wraparound():
         zf, _ = ops.fused_forward(ids.to(d), values.clone().to(d), tab, W.to(d), Q.to(d), Vv.to(d), alpha, ld=12, nemb=E)
     torch.cuda.synchronize()
     assert torch.equal(z1, z2)                                                     # deterministic
+    assert norm_rel(z1r.cpu(), z1.cpu()) <= 2e-6                                   # both thread mappings, one function
     assert ((z1 - zf).abs() <= 2e-5 * zf.abs() * max(1.0, zf.log().abs().max().item())).all()
     zb_ref = (z1 - post[0][None, :, None]) * post[1][None, :, None] + post[2][None, :, None]
     assert torch.allclose(zb, zb_ref, rtol=1e-6, atol=1e-6)
