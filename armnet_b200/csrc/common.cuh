@@ -30,7 +30,7 @@ int get_device_info(DeviceInfo *out);  // cached per device (read-only after fir
 // path); armnet_set_tuning() changes them afterwards (tests, A/B runs).  -1 = the library's own default.
 struct Tuning {
     int tmem;           // ARMNET_TMEM         1 / 0: force armnet_fwd_tmem_kernel on / off where the shape allows it
-    int tmem_rows;      // ARMNET_TMEM_ROWS    1 / 2: rows per thread of armnet_fwd_tmem_kernel (default 2 where K*O % 256 == 0)
+    int tmem_rows;      // ARMNET_TMEM_ROWS    1 / 2: rows per thread of armnet_fwd_tmem_kernel (default 1; 2 needs K*O % 256 == 0)
     int mma;            // ARMNET_MMA          1 / 0: force armnet_fwd_mma_kernel on / off
     int mma_split_rna;  // ARMNET_MMA_SPLIT=rna
     int mma_warps;      // ARMNET_MMA_WARPS    12: the 12-warp instance

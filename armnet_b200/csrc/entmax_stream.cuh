@@ -1,9 +1,10 @@
-// alpha-entmax + cross product for a thread that owns TWO rows whose logits stay in TENSOR MEMORY: every pass over a
-// row's F logits streams them from TMEM in chunks of 8 columns (tcgen05.ld.32x32b.x8, the next chunk in flight while
-// the current one is processed) instead of holding 2 x F registers.  Same algorithms, constants and stopping rules as
-// entmax_rows.cuh (reference: utils/entmax.py:29-68); see there for the maths.  What it buys: two rows per thread share
-// every shared-memory read of an embedding row (the kernel is bound by the shared-memory -> register return path when a
-// thread owns one row), at ~100 registers per thread.
+// Dense-row fast path for a thread that owns TWO rows whose logits stay in TENSOR MEMORY: every pass over a row's F
+// logits streams them from TMEM in chunks of 8 columns (tcgen05.ld.32x32b.x8) instead of holding 2 x F registers, so two
+// rows per thread share every shared-memory read of an embedding row at ~100 registers per thread (with one row per
+// thread the init-weight regime is bound by the shared-memory -> register return path).  Rows that are not near-uniform
+// take the register path of entmax_rows.cuh, one row at a time (measured: the streamed plain / pre-solve passes lose to
+// the register-resident ones, 13.5 M vs 15.5 M samples/s at the trained-like C2a regime).  Same algorithms, constants and
+// stopping rules as entmax_rows.cuh (reference: utils/entmax.py:29-68).
 #pragma once
 
 #include <type_traits>
@@ -11,6 +12,10 @@
 #include "entmax_rows.cuh"
 
 namespace armnet {
+
+#ifndef ARMNET_STREAM_UNROLL
+#define ARMNET_STREAM_UNROLL 5
+#endif
 
 __device__ __forceinline__ void tms_ld8(uint32_t taddr, float2 (&X)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -21,148 +26,106 @@ __device__ __forceinline__ void tms_ld8(uint32_t taddr, float2 (&X)[4]) {
 }
 __device__ __forceinline__ void tms_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Calls f(j, x0, x1) for j = 0 .. NP-1 with x_n = (X_n[2j], X_n[2j+1]) of the rows at TMEM addresses t0 / t1.
-// ODD: element (NP-1).y is padding and arrives as -inf.
+// Calls f(c, k, x0, x1) for chunk c = 0 .. NP/4-1 (a RUNTIME loop: the code of a pass is one chunk long, which keeps the
+// kernel inside the instruction cache) and pair k = 0 .. 3 (unrolled), field pair j = 4c + k, with
+// x_n = (X_n[2j], X_n[2j+1]) of the rows at TMEM addresses t0 / t1.  ODD: element (NP-1).y is padding and arrives as -inf.
 template <int NP, bool ODD, class F>
 __device__ __forceinline__ void tm_stream_rows2(uint32_t t0, uint32_t t1, F f) {
     static_assert(NP % 4 == 0, "chunks of 4 field pairs");
     constexpr int NC = NP / 4;
-    float2 a[2][4], b[2][4];
-    tms_ld8(t0, a[0]);
-    tms_ld8(t1, a[1]);
-    tms_ld_wait();
-#pragma unroll
+    constexpr int kUnroll = ARMNET_STREAM_UNROLL;
+#pragma unroll kUnroll
     for (int c = 0; c < NC; ++c) {
-        if (c + 1 < NC) {
-            tms_ld8(t0 + 8 * (c + 1), b[0]);
-            tms_ld8(t1 + 8 * (c + 1), b[1]);
-        }
+        // load, wait, use: the registers of an in-flight tcgen05.ld are never live across other work (the compiler does
+        // not know the load is asynchronous); the latency of a chunk is hidden by the CTA's other warps
+        float2 a[2][4];
+        tms_ld8(t0 + 8 * c, a[0]);
+        tms_ld8(t1 + 8 * c, a[1]);
+        tms_ld_wait();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float2 x0 = a[0][k], x1 = a[1][k];
-            if (ODD && 4 * c + k == NP - 1) x0.y = x1.y = neg_inf();
-            f(4 * c + k, x0, x1);
-        }
-        if (c + 1 < NC) {
-            tms_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                a[0][k] = b[0][k];
-                a[1][k] = b[1][k];
-            }
+            if (ODD && k == 3 && c == NC - 1) x0.y = x1.y = neg_inf();
+            f(c, k, x0, x1);
         }
     }
 }
 
-// Complete gates + cross product of two rows.  X holds their logits in registers for the passes that need no
-// accumulators (moments, maxima, pre-solve, plain Newton sweeps: entmax_rows.cuh at register speed); the passes that
-// accumulate the cross product re-stream the logits from tensor memory (t0 / t1) instead, so that the 2 x F logit
-// registers and the 2 x E accumulators are never live together.  Calls reset() before every pass that feeds
-// cross(j, w0, w1) (w_n = gates * values of row n for the field pair j); returns S[n], the normaliser of the gates the
-// LAST cross pass used.  vrow(n, j) = (V_n[2j], V_n[2j+1]).  All 32 lanes must call this together.
+// DENSE rows only (near-uniform logits: random-init weights, weakly attending neurons): gates + cross product of the two
+// rows at t0 / t1 with the logits streamed from tensor memory.  Returns false -- nothing accumulated -- when the rows are
+// not near-uniform or the mode is not POW_GENERAL; the caller then runs the register path (entmax_rows.cuh) row by row.
+// Otherwise: closed-form start tau0 = mean - cF + (q-1) var / (2 cF) (entmax.cuh), sweeps that accumulate
+// cross(c, k, w0, w1) (w_n = gates * values of row n for the field pair 4c + k; reset() is called before each) and verify
+// themselves with the q-norm Newton step, S[n] = the normaliser of the gates of the last sweep.
+// vrow(n, c, k) = (V_n[2j], V_n[2j+1]), j = 4c + k.  All 32 lanes call this together.
 template <int NP, bool ODD, class VRow, class Cross, class Reset>
-__device__ __forceinline__ void stream_entmax_cross(const float2 (&X)[2][NP], uint32_t t0, uint32_t t1,
-                                                    const EntmaxParams &ep, float (&tau)[2], float (&S)[2], VRow vrow,
-                                                    Cross cross, Reset reset) {
+__device__ __forceinline__ bool stream_dense_entmax_cross(uint32_t t0, uint32_t t1, const EntmaxParams &ep,
+                                                          float (&tau)[2], float (&S)[2], VRow vrow, Cross cross,
+                                                          Reset reset) {
     constexpr unsigned kFull = 0xffffffffu;
-    float mx[2], mean[2];
-    auto pass_cross = [&](auto mode_tag) {
-        constexpr int MODE = decltype(mode_tag)::value;
+    constexpr int NC = NP / 4;
+    if (ep.mode != POW_GENERAL) return false;
+    // mean and variance about a pivot (each row's first logit): no cancellation for near-uniform rows
+    {
+        float c0 = 0.f, c1 = 0.f;
+        float2 nc0 = make_float2(0.f, 0.f), nc1 = nc0, sa0 = nc0, sa1 = nc0, q0 = nc0, q1 = nc0;
+        tm_stream_rows2<NP, ODD>(t0, t1, [&](int c, int k, float2 x0, float2 x1) {
+            if (k == 0 && c == 0) {
+                c0 = x0.x;
+                c1 = x1.x;
+                nc0 = splat2(-c0);
+                nc1 = splat2(-c1);
+            }
+            float2 d0 = fadd2(x0, nc0), d1 = fadd2(x1, nc1);
+            if (ODD && k == 3 && c == NC - 1) d0.y = d1.y = 0.f;
+            sa0 = fadd2(sa0, d0);
+            sa1 = fadd2(sa1, d1);
+            q0 = ffma2(d0, d0, q0);
+            q1 = ffma2(d1, d1, q1);
+        });
+        const float md0 = (sa0.x + sa0.y) * ep.inv_F, md1 = (sa1.x + sa1.y) * ep.inv_F;
+        const float v0 = fmaxf(fmaf(-md0, md0, (q0.x + q0.y) * ep.inv_F), 0.f);
+        const float v1 = fmaxf(fmaf(-md1, md1, (q1.x + q1.y) * ep.inv_F), 0.f);
+        // F var <= (0.2 cF)^2 bounds every |X_f - mean| by 0.2 cF: every X_f - tau >= 0.8 cF > 0, no clamp in the sweep
+        if (!__all_sync(kFull, fmaxf(v0, v1) <= ep.uni_var)) return false;
+        tau[0] = c0 + md0 - ep.cF + ep.uni_k * v0;
+        tau[1] = c1 + md1 - ep.cF + ep.uni_k * v1;
+    }
+    const float2 qm1 = splat2(ep.qm1);
+#pragma unroll 1
+    for (int it = 0; it < 6; ++it) {
         const float2 nt0 = splat2(-tau[0]), nt1 = splat2(-tau[1]);
-        float2 s0 = make_float2(0.f, 0.f), s1 = s0;
+        float2 s0 = make_float2(0.f, 0.f), s1 = s0, g0 = s0, g1 = s0;   // sums of u^q and u^(q-1)
         reset();
-        tm_stream_rows2<NP, ODD>(t0, t1, [&](int j, float2 x0, float2 x1) {
-            const float2 p0 = gate_unnorm2<MODE>(x0, nt0, ep), p1 = gate_unnorm2<MODE>(x1, nt1, ep);
+        tm_stream_rows2<NP, ODD>(t0, t1, [&](int c, int k, float2 x0, float2 x1) {
+            float2 u0 = fadd2(x0, nt0), u1 = fadd2(x1, nt1);
+            if (ODD && k == 3) {   // only the padded element (-inf) needs the clamp
+                u0 = relu2(u0);
+                u1 = relu2(u1);
+            }
+            const float2 l0 = fmul2(make_float2(fast_lg2(u0.x), fast_lg2(u0.y)), qm1);
+            const float2 l1 = fmul2(make_float2(fast_lg2(u1.x), fast_lg2(u1.y)), qm1);
+            const float2 e0 = make_float2(fast_ex2(l0.x), fast_ex2(l0.y));   // u^(q-1); u = 0 -> 0 because q - 1 > 0
+            const float2 e1 = make_float2(fast_ex2(l1.x), fast_ex2(l1.y));
+            g0 = fadd2(g0, e0);
+            g1 = fadd2(g1, e1);
+            const float2 p0 = fmul2(e0, u0), p1 = fmul2(e1, u1);          // u^q
             s0 = fadd2(s0, p0);
             s1 = fadd2(s1, p1);
-            cross(j, fmul2(p0, vrow(0, j)), fmul2(p1, vrow(1, j)));
+            cross(c, k, fmul2(p0, vrow(0, c, k)), fmul2(p1, vrow(1, c, k)));   // armnet.py:36; normalised at the end
         });
         S[0] = s0.x + s0.y;
         S[1] = s1.x + s1.y;
-    };
-    if (ep.mode != POW_GENERAL) {
-        rows_max_mean<2, NP, ODD>(X, ep, mx, mean);
-        if (ep.mode == POW_SOFTMAX) {
-            tau[0] = mx[0];
-            tau[1] = mx[1];
-            pass_cross(std::integral_constant<int, POW_SOFTMAX>{});
-        } else {
-            rows_solve_simple<2, NP>(X, ep, mx, mean, tau);
-            if (ep.mode == POW_SQUARE)
-                pass_cross(std::integral_constant<int, POW_SQUARE>{});
-            else
-                pass_cross(std::integral_constant<int, POW_LINEAR>{});
-        }
-        return;
+        const float d0 = qnorm_newton_step(S[0], g0.x + g0.y, ep), d1 = qnorm_newton_step(S[1], g1.x + g1.y, ep);
+        const float a0 = fabsf(d0), a1 = fabsf(d1);
+        const float rel0 = 2.4e-7f * fabsf(tau[0]), rel1 = 2.4e-7f * fabsf(tau[1]);
+        // |dp| <= q u^(q-1) |d| before the renormalisation: inside the parity budget (gates 2e-6 abs)
+        if (__all_sync(kFull, a0 <= fmaxf(5e-7f, rel0) && a1 <= fmaxf(5e-7f, rel1))) return true;
+        // a Newton step moves tau by a tiny fraction of cF here, the rows stay dense
+        tau[0] += d0;
+        tau[1] += d1;
     }
-    // ---- POW_GENERAL, phase 1 (logits in registers)
-    // near-uniform rows (random-init weights / weakly attending neurons): closed-form start, every gate is positive
-    const bool dense = __all_sync(kFull, rows_moments_uniform<2, NP, ODD>(X, ep, mean, tau));
-    bool fuse = dense;
-    int it = 0;
-    if (!dense) {
-        rows_max<2, NP, ODD>(X, mx);
-        if (ep.q < 2.f) {
-            rows_holder_presolve<2, NP, 3>(X, ep, mx, mean, tau);
-        } else {
-            tau[0] = fmaxf(mx[0] - 1.f, mean[0] - ep.cF);
-            tau[1] = fmaxf(mx[1] - 1.f, mean[1] - ep.cF);
-        }
-        float S1[2];
-#pragma unroll 1
-        for (; it < 12; ++it) {
-            rows_general_sweep<2, NP, false>(X, tau, ep, S, S1, vrow, [](int, const float2 (&)[2]) {});
-            const float d0 = qnorm_newton_step(S[0], S1[0], ep), d1 = qnorm_newton_step(S[1], S1[1], ep);
-            const float a0 = fabsf(d0), a1 = fabsf(d1);
-            const float rel0 = 2.4e-7f * fabsf(tau[0]), rel1 = 2.4e-7f * fabsf(tau[1]);
-            tau[0] += d0;
-            tau[1] += d1;
-            // the step is applied even when it is the last: |f(tau + d)| = O(d^2), and the caller renormalises
-            if (__all_sync(kFull, a0 <= fmaxf(2e-5f, rel0) && a1 <= fmaxf(2e-5f, rel1))) break;
-            if (__all_sync(kFull, fmaxf(a0, a1) <= 3e-3f)) {   // the next sweep is predicted to be the last: fuse it
-                fuse = true;
-                ++it;
-                break;
-            }
-        }
-    }
-    // ---- phase 2 (logits streamed from tensor memory): sweeps that also accumulate the cross product
-    if (fuse) {
-        const float2 qm1 = splat2(ep.qm1);
-#pragma unroll 1
-        for (; it < 12; ++it) {
-            const float2 nt0 = splat2(-tau[0]), nt1 = splat2(-tau[1]);
-            float2 s0 = make_float2(0.f, 0.f), s1 = s0, g0 = s0, g1 = s0;   // sums of u^q and u^(q-1)
-            reset();
-            tm_stream_rows2<NP, ODD>(t0, t1, [&](int j, float2 x0, float2 x1) {
-                float2 u0 = fadd2(x0, nt0), u1 = fadd2(x1, nt1);
-                if (!dense || (ODD && j == NP - 1)) {   // dense rows: every X_f - tau >= 0.8 cF > 0, no clamp needed
-                    u0 = relu2(u0);
-                    u1 = relu2(u1);
-                }
-                const float2 l0 = fmul2(make_float2(fast_lg2(u0.x), fast_lg2(u0.y)), qm1);
-                const float2 l1 = fmul2(make_float2(fast_lg2(u1.x), fast_lg2(u1.y)), qm1);
-                const float2 e0 = make_float2(fast_ex2(l0.x), fast_ex2(l0.y));   // u^(q-1); u = 0 -> 0 because q - 1 > 0
-                const float2 e1 = make_float2(fast_ex2(l1.x), fast_ex2(l1.y));
-                g0 = fadd2(g0, e0);
-                g1 = fadd2(g1, e1);
-                const float2 p0 = fmul2(e0, u0), p1 = fmul2(e1, u1);          // u^q
-                s0 = fadd2(s0, p0);
-                s1 = fadd2(s1, p1);
-                cross(j, fmul2(p0, vrow(0, j)), fmul2(p1, vrow(1, j)));        // armnet.py:36; normalised once, at the end
-            });
-            S[0] = s0.x + s0.y;
-            S[1] = s1.x + s1.y;
-            const float d0 = qnorm_newton_step(S[0], g0.x + g0.y, ep), d1 = qnorm_newton_step(S[1], g1.x + g1.y, ep);
-            const float a0 = fabsf(d0), a1 = fabsf(d1);
-            const float rel0 = 2.4e-7f * fabsf(tau[0]), rel1 = 2.4e-7f * fabsf(tau[1]);
-            // |dp| <= q u^(q-1) |d| before the renormalisation: inside the parity budget (gates 2e-6 abs)
-            if (__all_sync(kFull, a0 <= fmaxf(5e-7f, rel0) && a1 <= fmaxf(5e-7f, rel1))) return;
-            tau[0] += d0;
-            tau[1] += d1;
-        }
-    }
-    pass_cross(std::integral_constant<int, POW_GENERAL>{});
+    return true;   // six self-correcting sweeps: the last accumulators are within the parity budget
 }
 
 }  // namespace armnet

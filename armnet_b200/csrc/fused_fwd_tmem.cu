@@ -145,9 +145,10 @@ int tmem_launch(const char *who, const void *ids, int ids_i32, float *values, co
     P.n_tiles = (int)((B + 1) / 2);
     P.row_bytes = (E * 4 + 15) / 16 * 16;
     P.tma_store = ((uintptr_t)out_z % 16 == 0) ? 1 : 0;
-    // rows per thread: 2 (logits streamed from tensor memory) when K*O % 256 == 0, unless tuning "tmem_rows" == 1 asks
-    // for the one-row mapping (logits in registers)
-    const int NR = (R % 256 == 0 && tuning().tmem_rows != 1) ? 2 : 1;
+    // rows per thread: 1 (logits in registers) by default.  tuning "tmem_rows" == 2 (needs K*O % 256 == 0): two rows per
+    // thread, dense rows streamed from tensor memory -- +4 % in the init-weight regime (34.9 M vs 33.5 M samples/s at
+    // C2a), -10 % with sparse gates (13.9 M vs 15.5 M), so it is not the default (profiles/r2_v3_summary.md)
+    const int NR = (R % 256 == 0 && tuning().tmem_rows == 2) ? 2 : 1;
     // gather look-ahead: as deep as the raw ring that fits (<= 16 tiles = 32 samples: the mbarrier block holds 32)
     int look = 16;
     for (; look >= 1; --look) {

@@ -454,13 +454,13 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
                 const unsigned char *eb = tiles + bt * L.tile_bytes + s * (NFP * 128);
                 const float4 *vr0 = reinterpret_cast<const float4 *>(Vs + (size_t)r0 * L.vstr);
                 const float4 *vr1 = reinterpret_cast<const float4 *>(Vs + (size_t)(r0 + 128) * L.vstr);
-                auto vrow = [&](int n, int j) -> float2 {
-                    const float4 v4 = (n ? vr1 : vr0)[j >> 1];
-                    return (j & 1) ? make_float2(v4.z, v4.w) : make_float2(v4.x, v4.y);
+                // field pair j = 4c + k (c: runtime chunk, k: unrolled): V pairs (2j, 2j+1) sit in float4 2c + (k >> 1) of the
+                // row; e rows f = 8c + 2k, 8c + 2k + 1 are 1024 c bytes into the sample's rows, swizzle f & 7 = 2k, 2k + 1
+                auto vrow = [&](int n, int c, int k) -> float2 {
+                    const float4 v4 = (n ? vr1 : vr0)[2 * c + (k >> 1)];
+                    return (k & 1) ? make_float2(v4.z, v4.w) : make_float2(v4.x, v4.y);
                 };
-                auto fma_field = [&](int f, float w0, float w1) {
-                    const unsigned char *row = eb + f * 128;
-                    const int sw = f & 7;
+                auto fma_field = [&](const unsigned char *row, int sw, float w0, float w1) {
                     const float4 c0 = *reinterpret_cast<const float4 *>(row + ((0 ^ sw) << 4));
                     const float4 c1 = *reinterpret_cast<const float4 *>(row + ((1 ^ sw) << 4));
                     const float2 c2 = *reinterpret_cast<const float2 *>(row + ((2 ^ sw) << 4));
@@ -473,25 +473,66 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
                         acc[1][x] = ffma2(bw, e2[x], acc[1][x]);
                     }
                 };
-                auto cross = [&](int j, float2 w0, float2 w1) {
-                    fma_field(2 * j, w0.x, w1.x);
-                    if (!ODD || j < NP - 1) fma_field(2 * j + 1, w0.y, w1.y);
+                auto cross = [&](int c, int k, float2 w0, float2 w1) {
+                    const unsigned char *rows8 = eb + c * (8 * 128);
+                    fma_field(rows8 + (2 * k) * 128, 2 * k, w0.x, w1.x);
+                    if (!ODD || k < 3 || c < NP / 4 - 1) fma_field(rows8 + (2 * k + 1) * 128, 2 * k + 1, w0.y, w1.y);
                 };
                 auto reset = [&]() {
 #pragma unroll
                     for (int x = 0; x < EL / 2; ++x) acc[0][x] = acc[1][x] = make_float2(0.f, 0.f);
                 };
-                float2 X[2][NP];   // phase-1 copy of the logits (entmax_stream.cuh); the cross passes re-stream them
+                if (!stream_dense_entmax_cross<NP, ODD>(t0, t0 + 2 * NFP, ep, tau, S, vrow, cross, reset)) {
+                    // not near-uniform (or alpha in {1, 1.5, 2}): one row at a time with its logits in registers
+#pragma unroll 1
+                    for (int n = 0; n < 2; ++n) {
+                        float2 X[1][NP];
+                        const uint32_t tn = t0 + (uint32_t)(n * 2 * NFP);
+                        if (NP >= 16) tm_ld32(tn, &X[0][0]);
 #pragma unroll
-                for (int n = 0; n < 2; ++n) {
-                    const uint32_t tn = t0 + (uint32_t)(n * 2 * NFP);
-                    if (NP >= 16) tm_ld32(tn, &X[n][0]);
+                        for (int j = (NP >= 16 ? 16 : 0); j < NP; j += 4) tm_ld8(tn + 2 * j, &X[0][j]);
+                        tm_ld_wait();
+                        if (ODD) X[0][NP - 1].y = neg_inf();
+                        const float4 *vr = n ? vr1 : vr0;
+                        float2 a1[EL / 2];
+                        float tau1[1], S1r[1] = {1.f};
+                        auto vrow1 = [&](int, int j) -> float2 {
+                            const float4 v4 = vr[j >> 1];
+                            return (j & 1) ? make_float2(v4.z, v4.w) : make_float2(v4.x, v4.y);
+                        };
+                        auto fma1 = [&](int f, float w) {
+                            const unsigned char *row = eb + f * 128;
+                            const int sw = f & 7;
+                            const float4 c0 = *reinterpret_cast<const float4 *>(row + ((0 ^ sw) << 4));
+                            const float4 c1 = *reinterpret_cast<const float4 *>(row + ((1 ^ sw) << 4));
+                            const float2 c2 = *reinterpret_cast<const float2 *>(row + ((2 ^ sw) << 4));
+                            const float2 w2 = splat2(w);
+                            a1[0] = ffma2(w2, make_float2(c0.x, c0.y), a1[0]);
+                            a1[1] = ffma2(w2, make_float2(c0.z, c0.w), a1[1]);
+                            a1[2] = ffma2(w2, make_float2(c1.x, c1.y), a1[2]);
+                            a1[3] = ffma2(w2, make_float2(c1.z, c1.w), a1[3]);
+                            a1[4] = ffma2(w2, c2, a1[4]);
+                        };
+                        auto cross1 = [&](int j, const float2 (&w)[1]) {
+                            fma1(2 * j, w[0].x);
+                            if (!ODD || j < NP - 1) fma1(2 * j + 1, w[0].y);
+                        };
+                        auto reset1 = [&]() {
 #pragma unroll
-                    for (int j = (NP >= 16 ? 16 : 0); j < NP; j += 4) tm_ld8(tn + 2 * j, &X[n][j]);
+                            for (int x = 0; x < EL / 2; ++x) a1[x] = make_float2(0.f, 0.f);
+                        };
+                        rows_entmax_cross<1, NP, ODD>(X, ep, tau1, S1r, vrow1, cross1, reset1);
+                        if (n == 0) {
+#pragma unroll
+                            for (int x = 0; x < EL / 2; ++x) acc[0][x] = a1[x];
+                            S[0] = S1r[0];
+                        } else {
+#pragma unroll
+                            for (int x = 0; x < EL / 2; ++x) acc[1][x] = a1[x];
+                            S[1] = S1r[0];
+                        }
+                    }
                 }
-                tm_ld_wait();
-                if (ODD) X[0][NP - 1].y = X[1][NP - 1].y = neg_inf();
-                stream_entmax_cross<NP, ODD>(X, t0, t0 + 2 * NFP, ep, tau, S, vrow, cross, reset);
             }
             // logits and e rows are not read any more: hand the D slot and the tile back (one arrival per unit each)
             tm_fence_before();
