@@ -129,7 +129,11 @@ static size_t pair_tables_bytes(const FwdInstance *I, int K, int O) {
 }
 // Does this call run on armnet_fwd_tmem_kernel?  (shape, solver, 16-byte table rows, no validation outputs)
 static bool use_tmem_kernel(int F, int E, int R, int mode) {
-    return tuning().tmem != 0 && mode != POW_BISECT && tmem_shape_supported(F, E, R);
+    // default: only for a general alpha (MUFU-bound entmax), where it measured faster than armnet_fwd_kernel on B200
+    // (C2a: 33.6 M vs 28.1 M samples/s); at alpha = 2 / 1.5 (no MUFU in the solver) armnet_fwd_kernel wins
+    // (C2b: 49.5 M vs 41.5 M).  tuning "tmem" = 1 forces it wherever the shape allows, 0 switches it off.
+    if (tuning().tmem == 0 || mode == POW_BISECT || !tmem_shape_supported(F, E, R)) return false;
+    return tuning().tmem == 1 || mode == POW_GENERAL;
 }
 }  // namespace armnet
 

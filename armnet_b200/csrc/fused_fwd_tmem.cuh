@@ -20,7 +20,7 @@
 //     pre-solve, q-norm Newton, last sweep fused with the cross product), s[x] = sum_f p_f V_f e[f,x] on FFMA2 with the
 //     e rows read (warp-broadcast) from the B tile itself -- its first 10 floats are the exact fp32 e --, exp, optional
 //     eval-mode arm_bn, one TMA bulk store per warp-unit (64 consecutive neurons x E of one sample).
-// Roles: 12 consumer warps (3 per TMEM lane quadrant; units = (item, quadrant, sample) taken in order from one counter
+// Roles: 16 consumer warps (4 per TMEM lane quadrant; units = (item, quadrant, sample) taken in order from one counter
 // per quadrant) + three producer warps that only meet through mbarriers: the GATHER warp prefetches ids / values (clamp
 // in place, range check) and issues the TMA bulk row gathers up to 16 tiles ahead into a raw ring; the CONVERT warp turns
 // landed rows into B-tile rows (scale by the value: e = T[id] v exactly as layers.py:21; split; swizzled store); the MMA
@@ -39,15 +39,18 @@
 namespace armnet {
 
 #ifndef ARMNET_TMEM_CONSUMERS
-#define ARMNET_TMEM_CONSUMERS 12
+#define ARMNET_TMEM_CONSUMERS 16
 #endif
 constexpr int kTmConsumers = ARMNET_TMEM_CONSUMERS;   // consumer warps (a multiple of 4: TMEM lane quadrants)
 #ifndef ARMNET_TMEM_SETMAXNREG
 #define ARMNET_TMEM_SETMAXNREG 0
 #endif
-// 16 warps = 12 consumers + the producer warpgroup: gather warp, convert warp, MMA warp (+ 1 idle).  4 warps per SM
-// sub-partition -> 128 registers per thread.  ARMNET_TMEM_SETMAXNREG (experiment): the producer warpgroup gives registers
-// back and the consumers grow to 160.
+// 20 warps = 16 consumers (4 per TMEM lane quadrant) + the producer warpgroup: gather warp, convert warp, MMA warp
+// (+ 1 idle).  5 warps per SM sub-partition -> 96 registers per thread: 40 logit + 10 accumulator registers leave room
+// for the software pipelining of the sweeps.  Measured at C2a (profiles/r2_v3_summary.md): 12 consumers x 128 registers
+// 33.5 M / 15.5 M samples/s (init / trained-like), 16 x 96: 35.2 M / 16.1 M, 20 x 80: 34.3 M / 16.2 M.
+// ARMNET_TMEM_SETMAXNREG (experiment, no gain: ptxas keeps the launch-bound register cap): the producer warpgroup gives
+// registers back and the consumers grow.
 constexpr int kTmWarpGather = kTmConsumers, kTmWarpConvert = kTmConsumers + 1, kTmWarpMma = kTmConsumers + 2;
 constexpr int kTmThreads = (kTmConsumers + 4) * 32;
 constexpr int kTmTiles = 4;                           // B-tile ring (tiles of 2 samples)

@@ -154,7 +154,7 @@ int armnet_fused_bwd_supported(int F, int E);
  * K*O % 64 == 0, a compiled field / nemb bucket (33-40 fields, nemb 10 or 16) and a Newton-type solver; default only
  * where it measured faster on B200: nemb 16), 3 = armnet_fwd_tmem_kernel (attention logits as tcgen05.mma into tensor
  * memory, entmax with the MUFU-free pre-solve, csrc/fused_fwd_tmem.cuh; needs 39 or 40 fields, nemb <= 10, K*O a multiple
- * of 256 and <= 768, a Newton-type solver; at run time also 16-byte-aligned table rows and no validation outputs,
+ * of 128 and <= 768, a Newton-type solver; chosen by default for a general alpha only (1 < alpha < 2, alpha != 1.5); at run time also 16-byte-aligned table rows and no validation outputs,
  * otherwise the call falls back to kind 1 / 2).  armnet_set_tuning("tmem" / "mma", 1 / 0 / -1) forces a kind on / off /
  * back to the default; the ARMNET_TMEM / ARMNET_MMA environment variables give the initial values (read once). */
 int armnet_fused_fwd_kernel_kind(int F, int E, int K, int O, float alpha, int solver);

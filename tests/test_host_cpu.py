@@ -171,8 +171,14 @@ def test_fused_kernel_selection_is_host_logic():
         ops.set_tuning('tmem', -1)
         ops.set_tuning('mma', -1)
         assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7) == 3       # C2a
-        assert ops.fused_fwd_kernel_kind(39, 10, 4, 64, 2.0) == 3        # C2b
-        assert ops.fused_fwd_kernel_kind(40, 8, 2, 128, 1.5) == 3
+        assert ops.fused_fwd_kernel_kind(40, 8, 3, 128, 1.3) == 3        # K*O = 384, general alpha
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 64, 2.0) == 1        # C2b: alpha = 2 -> armnet_fwd_kernel by default
+        assert ops.fused_fwd_kernel_kind(40, 8, 2, 128, 1.5) == 1
+        ops.set_tuning('tmem', 1)
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 64, 2.0) == 3        # forced on
+        assert ops.fused_fwd_kernel_kind(40, 8, 2, 128, 1.0) == 3
+        assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 2.5) == 1       # never with the literal bisection
+        ops.set_tuning('tmem', -1)
         assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 2.5) == 1       # alpha > 2 -> literal bisection
         assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7, ops.SOLVER_BISECT) == 1
         assert ops.fused_fwd_kernel_kind(39, 10, 4, 100, 1.7) == 1       # K*O % 256 != 0
