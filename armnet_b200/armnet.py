@@ -77,7 +77,10 @@ class ARMNetModel(nn.Module):
             nn.init.constant_(self.ensemble_layer.bias, 0.)
         # host-side knobs (not parameters, not in state_dict)
         self.padded_table = True     # keep a 16-byte-aligned shadow table for TMA row gathers in no-grad mode
-        self.validate_ids = False    # synchronising id-range check after each forward (reference: IndexError)
+        # id-range check (reference: IndexError on CPU, device assert on CUDA, layers.py:20).  'lazy' (default): the kernels
+        # record a bad id in a device flag at no cost and check_ids() / BatchScorer.result() / train.py's end-of-split report
+        # raise IndexError -- no per-batch synchronisation; True: synchronising check after every forward; False: off
+        self.validate_ids = 'lazy'
         self.solver = ops.SOLVER_AUTO
         self.fuse_bn = True          # eval mode: apply arm_bn in the kernel epilogue
         self.fused_backward = True   # training: fused backward kernel (else unfused autograd stages)
@@ -129,9 +132,15 @@ class ARMNetModel(nn.Module):
                                      one_head=self.one_head, solver=self.solver, ld=ld, nemb=table.shape[1],
                                      err_flag=self._err_flag if self.validate_ids else None,
                                      post=self._folded_bn() if fold_bn else None, prepared=prepared, **want)
-        if self.validate_ids:
+        if self.validate_ids is True:
             ops.raise_if_bad_ids(self._err_flag)
         return (z, extra) if want else z
+
+    def check_ids(self):
+        """Raise IndexError if any forward since the last check met an id outside [0, nfeat) (one synchronisation).
+        With validate_ids = 'lazy' this is where the reference's IndexError (layers.py:20) surfaces."""
+        if self._err_flag is not None:
+            ops.raise_if_bad_ids(self._err_flag)
 
     def _interaction_autograd(self, x):
         """Training: fused forward + fused backward kernels (ops.fused_interaction) when a backward instance exists

@@ -54,7 +54,7 @@ class ARMNetModel(_MultiHead):
             nn.init.constant_(self.ensemble_layer.weight, 0.5)
             nn.init.constant_(self.ensemble_layer.bias, 0.)
         self.padded_table = True
-        self.validate_ids = False
+        self.validate_ids = 'lazy'
         self.solver = ops.SOLVER_AUTO
         self.fuse_bn = True
         self.fused_backward = True

@@ -221,13 +221,13 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
     if (rc != ARMNET_OK) return rc;
 
     const int R = K * O;
-    const int R2 = (R + 1) / 2;
     const int ES = I->ES;
     const int E_lanes = I->EC * ES;
     const int E_stride = round_up(E_lanes, 4);
     const int mstr = E_lanes | 1, vstr = I->FP | 1;
+    const int R2_all = (R + 1) / 2;
     float *Mg2 = (float *)workspace;
-    float *Vg2 = Mg2 + ((size_t)R2 * mstr * 8 + 15) / 16 * 4;  // 16-byte padded M table, then V
+    float *Vg2 = Mg2 + ((size_t)R2_all * mstr * 8 + 15) / 16 * 4;  // 16-byte padded M table, then V
     if ((post_scale != nullptr) != (post_mean != nullptr) || (post_scale != nullptr) != (post_shift != nullptr)) {
         set_error("%s: post_mean/post_scale/post_shift must be given together", who);
         return ARMNET_ERR_NULL;
@@ -236,11 +236,6 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
     P.ids = ids;
     P.values = values;
     P.table = table;
-    P.Mg2 = (const float2 *)Mg2;
-    P.Vg2 = (const float2 *)Vg2;
-    P.post_mean = post_mean;
-    P.post_scale = post_scale;
-    P.post_shift = post_shift;
     P.out_z = out_z;
     P.out_tau = out_tau;
     P.out_p = out_p;
@@ -261,8 +256,6 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
     P.B = B;
     P.F = F;
     P.E = E;
-    P.R = R;
-    P.R2 = R2;
     P.ids_i32 = ids_i32;
     P.clamp = clamp;
     P.clamp_inplace = clamp_inplace;
@@ -270,69 +263,7 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
     P.clamp_hi = clamp_hi;
     const float scale = (float)pow((double)D, -0.5);  // armnet.py:15 `d_k ** -0.5`, rounded to fp32 at use (:34)
     P.g_unscale = 1.f / P.ep.am1;
-
-    // ---- launch geometry (fused_fwd.cuh): tiles of SPG samples, UPG warp-units per tile, NW warps per CTA
-    const int PPW = 32 / ES;  // row pairs per warp-unit
-    if (R2 >= PPW) {
-        P.SPG = 1;
-        P.UPG = (R2 + PPW - 1) / PPW;
-    } else {
-        P.SPG = PPW / R2;  // several whole samples per unit
-        P.UPG = 1;
-        long long cap = (B + di.sm_count - 1) / di.sm_count;  // keep every SM busy on small batches
-        if (cap < 1) cap = 1;
-        if (P.SPG > cap) P.SPG = (int)cap;
-    }
-    const long long n_tiles = (B + P.SPG - 1) / P.SPG;
-    if (n_tiles > 0x7fffffffLL / P.UPG) {
-        set_error("%s: batch too large", who);
-        return ARMNET_ERR_SHAPE;
-    }
-    P.n_tiles = (int)n_tiles;
-    const unsigned grid = (unsigned)(n_tiles < di.sm_count ? n_tiles : di.sm_count);
-    const long long units_per_cta = (n_tiles + grid - 1) / grid * P.UPG;
-    P.NW = (int)(units_per_cta < max_warps ? units_per_cta : max_warps);
-    if (tuning().force_nw >= 1 && tuning().force_nw <= max_warps) P.NW = tuning().force_nw;  // tuning experiments only
-    P.lockstep = tuning().lockstep ? 1 : 0;  // default: units handed out dynamically
-
-    // ---- TMA eligibility
-    P.row_bytes = round_up(E * 4, 16);
-    P.tma_gather = ((ld * 4) % 16 == 0 && (uintptr_t)table % 16 == 0 && P.row_bytes <= ld * 4) ? 1 : 0;
-    if (tuning().no_tma_gather) P.tma_gather = 0;
-    // a unit's output rows are contiguous when pairs never straddle samples (R even); 16-byte size/alignment of each
-    // bulk store is re-checked per unit in the kernel
-    P.tma_store = (!bwd && !tuning().no_tma_store && R % 2 == 0 && (uintptr_t)out_z % 16 == 0) ? 1 : 0;
-
-    // ---- shared-memory budget: ids/values of an epoch of tiles are preloaded; the rest of the space becomes gather
-    // slots (the deeper the ring, the further ahead the TMA gathers run)
-    const int n_local_max = (int)((n_tiles + grid - 1) / grid);
-    const int in_flight = (P.NW + P.UPG - 1) / P.UPG;  // tiles being consumed at once
-    const int rows_pad = round_up(P.SPG * F, 4);
-    P.TPE = n_local_max;
-    if ((long long)P.TPE * rows_pad * 8 > 32 * 1024) P.TPE = (32 * 1024) / (rows_pad * 8);
-    if (P.TPE < 1) P.TPE = 1;
-    int best_slots = 0;
-    for (int ns = kMaxSlots; ns >= in_flight + 2; --ns) {
-        P.n_slots = ns;
-        const SmemLayout Lt(I->FP, E_lanes, E_stride, ES, P, bwd != nullptr);
-        if (Lt.total <= di.smem_optin) {
-            best_slots = ns;
-            break;
-        }
-    }
-    if (best_slots == 0) {
-        P.n_slots = in_flight + 2;
-        const SmemLayout Lt(I->FP, E_lanes, E_stride, ES, P, bwd != nullptr);
-        set_error("%s: F=%d E=%d K*O=%d needs %d bytes of shared memory per CTA (limit %d)", who, F, E, R, Lt.total,
-                  di.smem_optin);
-        return ARMNET_ERR_UNSUPPORTED;
-    }
-    if (best_slots > n_local_max + in_flight + 1) best_slots = n_local_max + in_flight + 1;  // no more than useful
-    if (best_slots < in_flight + 2) best_slots = in_flight + 2;
-    P.n_slots = best_slots;
-    P.look = P.n_slots - in_flight - 1;
-    if (tuning().force_look >= 1 && tuning().force_look <= P.look) P.look = tuning().force_look;  // experiments only
-    const SmemLayout L(I->FP, E_lanes, E_stride, ES, P, bwd != nullptr);
+    P.R_out = R;
 
     cudaStream_t st = (cudaStream_t)stream;
     // armnet_fwd_tmem_kernel: logits on tcgen05 (fused_fwd_tmem.cuh).  Its operands live after the pair tables.
@@ -340,14 +271,116 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
     const bool tmem_ok = tmem_shape_supported(F, E, R) && P.ep.mode != POW_BISECT;
     const bool tmem_run = !bwd && use_tmem_kernel(F, E, R, P.ep.mode) && !out_tau && !out_p && !out_g && !out_s &&
                           (ld * 4) % 16 == 0 && (uintptr_t)table % 16 == 0 && ((E * 4 + 15) / 16 * 16) <= ld * 4;
+
+    // ---- launch geometry of armnet_fwd_kernel / armnet_fwd_mma_kernel for the rows [r_off, r_off + Rc) of every sample.
+    // Returns ARMNET_ERR_UNSUPPORTED (without an error text) when the tables of Rc rows do not fit shared memory.
+    const int PPW = 32 / ES;  // row pairs per warp-unit
+    unsigned grid = 0;
+    int smem_total = 0;
+    auto plan = [&](int r_off, int Rc) -> int {
+        const int R2 = (Rc + 1) / 2;
+        P.R = Rc;
+        P.R2 = R2;
+        P.r_off = r_off;
+        P.Mg2 = (const float2 *)(Mg2 + (size_t)(r_off / 2) * mstr * 2);
+        P.Vg2 = (const float2 *)(Vg2 + (size_t)(r_off / 2) * vstr * 2);
+        P.post_mean = post_mean ? post_mean + r_off : nullptr;
+        P.post_scale = post_scale ? post_scale + r_off : nullptr;
+        P.post_shift = post_shift ? post_shift + r_off : nullptr;
+        if (R2 >= PPW) {
+            P.SPG = 1;
+            P.UPG = (R2 + PPW - 1) / PPW;
+        } else {
+            P.SPG = PPW / R2;  // several whole samples per unit
+            P.UPG = 1;
+            long long cap = (B + di.sm_count - 1) / di.sm_count;  // keep every SM busy on small batches
+            if (cap < 1) cap = 1;
+            if (P.SPG > cap) P.SPG = (int)cap;
+        }
+        const long long n_tiles = (B + P.SPG - 1) / P.SPG;
+        if (n_tiles > 0x7fffffffLL / P.UPG) {
+            set_error("%s: batch too large", who);
+            return ARMNET_ERR_SHAPE;
+        }
+        P.n_tiles = (int)n_tiles;
+        grid = (unsigned)(n_tiles < di.sm_count ? n_tiles : di.sm_count);
+        const long long units_per_cta = (n_tiles + grid - 1) / grid * P.UPG;
+        P.NW = (int)(units_per_cta < max_warps ? units_per_cta : max_warps);
+        if (tuning().force_nw >= 1 && tuning().force_nw <= max_warps) P.NW = tuning().force_nw;  // tuning experiments only
+        P.lockstep = tuning().lockstep ? 1 : 0;  // default: units handed out dynamically
+
+        // TMA eligibility
+        P.row_bytes = round_up(E * 4, 16);
+        P.tma_gather = ((ld * 4) % 16 == 0 && (uintptr_t)table % 16 == 0 && P.row_bytes <= ld * 4) ? 1 : 0;
+        if (tuning().no_tma_gather) P.tma_gather = 0;
+        // a unit's output rows are contiguous when pairs never straddle samples (R even); 16-byte size/alignment of each
+        // bulk store is re-checked per unit in the kernel
+        P.tma_store = (!bwd && !tuning().no_tma_store && Rc % 2 == 0 && (uintptr_t)out_z % 16 == 0) ? 1 : 0;
+
+        // shared-memory budget: ids/values of an epoch of tiles are preloaded; the rest of the space becomes gather
+        // slots (the deeper the ring, the further ahead the TMA gathers run)
+        const int n_local_max = (int)((n_tiles + grid - 1) / grid);
+        const int in_flight = (P.NW + P.UPG - 1) / P.UPG;  // tiles being consumed at once
+        const int rows_pad = round_up(P.SPG * F, 4);
+        P.TPE = n_local_max;
+        if ((long long)P.TPE * rows_pad * 8 > 32 * 1024) P.TPE = (32 * 1024) / (rows_pad * 8);
+        if (P.TPE < 1) P.TPE = 1;
+        int best_slots = 0;
+        for (int ns = kMaxSlots; ns >= in_flight + 2; --ns) {
+            P.n_slots = ns;
+            const SmemLayout Lt(I->FP, E_lanes, E_stride, ES, P, bwd != nullptr);
+            if (Lt.total <= di.smem_optin) {
+                best_slots = ns;
+                break;
+            }
+        }
+        if (best_slots == 0) {
+            P.n_slots = in_flight + 2;
+            const SmemLayout Lt(I->FP, E_lanes, E_stride, ES, P, bwd != nullptr);
+            smem_total = Lt.total;
+            return ARMNET_ERR_UNSUPPORTED;
+        }
+        if (best_slots > n_local_max + in_flight + 1) best_slots = n_local_max + in_flight + 1;  // no more than useful
+        if (best_slots < in_flight + 2) best_slots = in_flight + 2;
+        P.n_slots = best_slots;
+        P.look = P.n_slots - in_flight - 1;
+        if (tuning().force_look >= 1 && tuning().force_look <= P.look) P.look = tuning().force_look;  // experiments only
+        const SmemLayout L(I->FP, E_lanes, E_stride, ES, P, bwd != nullptr);
+        smem_total = L.total;
+        return ARMNET_OK;
+    };
+
+    // K*O tiling: when the tables of all K*O rows do not fit one CTA's shared memory (large --h x --nattn_head), the plain
+    // forward runs in passes over row chunks (each pass gathers the batch again: 2 KB per sample against 40 B per row of
+    // output).  Validation outputs and the backward need the whole row range in one pass.
+    int chunk = R;
+    rc = tmem_run ? ARMNET_OK : plan(0, R);
+    if (rc == ARMNET_ERR_UNSUPPORTED) {
+        const bool can_tile = !bwd && !out_tau && !out_p && !out_g && !out_s;
+        if (can_tile) {
+            chunk = (R / 2) / 64 * 64;
+            for (; chunk >= 64; chunk -= 64)
+                if (plan(0, chunk) == ARMNET_OK) break;
+        }
+        if (!can_tile || chunk < 64) {
+            set_error("%s: F=%d E=%d K*O=%d needs %d bytes of shared memory per CTA (limit %d)", who, F, E, R, smem_total,
+                      di.smem_optin);
+            return ARMNET_ERR_UNSUPPORTED;
+        }
+        kernel = I->kernel;          // the tiled passes always run on armnet_fwd_kernel
+        max_warps = kMaxWarps;
+    } else if (rc != ARMNET_OK) {
+        return rc;
+    }
+
     if (mode != 2) {
         int n_prep = 0;
         if (mode == 1 || !tmem_run) {  // the pair tables (a mode-1 workspace must serve every kernel kind)
-            const int total = R2 * (mstr + vstr) * 2;
+            const int total = R2_all * (mstr + vstr) * 2;
             int blocks = (total + 255) / 256;
             if (blocks > di.sm_count * 4) blocks = di.sm_count * 4;
             attn_prepare_kernel<<<blocks, 256, 0, st>>>(bilinear_w, query, att_values, w_is_linear_layout, F, E, D, O, R,
-                                                         R2, E_lanes, mstr, vstr, scale, P.ep.am1, Mg2, Vg2);
+                                                         R2_all, E_lanes, mstr, vstr, scale, P.ep.am1, Mg2, Vg2);
             ARMNET_CUDA_TRY(cudaGetLastError());
             ++n_prep;
         }
@@ -369,9 +402,22 @@ static int launch_fused(const char *who, const BwdArgs *bwd, const void *ids, in
         return ARMNET_OK;
     }
     ARMNET_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
-    void *args[] = {(void *)&P};
-    ARMNET_CUDA_TRY(cudaLaunchKernel(kernel, dim3(grid), dim3(P.NW * 32), args, (size_t)L.total, st));
-    note_launches(mode == 2 ? 1 : 2);
+    int n_launch = 0;
+    for (int r_off = 0; r_off < R; r_off += chunk) {
+        const int Rc = (R - r_off < chunk) ? R - r_off : chunk;
+        rc = plan(r_off, Rc);
+        if (rc != ARMNET_OK) {
+            if (rc == ARMNET_ERR_UNSUPPORTED)
+                set_error("%s: F=%d E=%d rows %d..%d need %d bytes of shared memory per CTA (limit %d)", who, F, E, r_off,
+                          r_off + Rc, smem_total, di.smem_optin);
+            return rc;
+        }
+        if (r_off > 0) P.clamp_inplace = 0;   // the values were clamped (and written back) by the first pass
+        void *args[] = {(void *)&P};
+        ARMNET_CUDA_TRY(cudaLaunchKernel(kernel, dim3(grid), dim3(P.NW * 32), args, (size_t)smem_total, st));
+        ++n_launch;
+    }
+    note_launches((mode == 2 ? 0 : 1) + n_launch);
     return ARMNET_OK;
 }
 

@@ -64,6 +64,7 @@ struct FwdParams {
     int *err_flag;
     long long V, ld, B;
     int F, E, R, R2;
+    int R_out, r_off;  // out_z holds R_out rows per sample; this launch computes rows [r_off, r_off + R) (K*O tiling)
     int ids_i32;
     int clamp, clamp_inplace;
     float clamp_lo, clamp_hi;
@@ -727,7 +728,7 @@ __global__ void __launch_bounds__(BWD ? kBwdWarps * 32 : kMaxThreads, 1)
         }
         // the unit's rows [2*p_first, 2*min(p_first+PPW, n_pairs)) of the tile are contiguous in out_z when R is even
         const int pairs_here = min(PPW, n_pairs - p_first);
-        float *gdst = P.out_z + (b0 * R + 2LL * p_first) * (long long)E;
+        float *gdst = P.out_z + (b0 * P.R_out + P.r_off + 2LL * p_first) * (long long)E;   // SPG == 1 whenever R < R_out
         const uint32_t bytes = (uint32_t)(pairs_here * kNR * E * 4);
         if (P.tma_store && ((bytes | (uint32_t)reinterpret_cast<uintptr_t>(gdst)) & 15u) == 0) {
             if (lane == 0) tma_store_wait_read<0>();  // this warp's previous bulk store has drained the buffer
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(BWD ? kBwdWarps * 32 : kMaxThreads, 1)
                 tma_store_commit();
             }
         } else if (valid) {
-            float *dst = P.out_z + grow * E + c * EC;
+            float *dst = P.out_z + ((b0 + bl) * (long long)P.R_out + P.r_off + r0) * E + c * EC;
 #pragma unroll
             for (int x = 0; x < EC; ++x) {
                 if (c * EC + x < E) {

@@ -37,6 +37,7 @@ class _Slot:
         self.vals = torch.ones(B, F, dtype=torch.float32, device=dev)
         self.y_host = None
         self.y_dev = None
+        self.flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()   # copy of the model's bad-id flag, per batch
         self.graph = None
         self.ev_in = torch.cuda.Event()
         self.ev_done = torch.cuda.Event()
@@ -50,8 +51,8 @@ class BatchScorer:
             raise RuntimeError('BatchScorer needs the model on a CUDA device (armnet_b200 has no CPU path)')
         if model.training:
             raise RuntimeError('BatchScorer scores in eval mode: call model.eval() first')
-        if getattr(model, 'validate_ids', False):
-            raise RuntimeError('validate_ids synchronises every batch; check ids upstream or use model(x) directly')
+        if getattr(model, 'validate_ids', False) is True:
+            raise RuntimeError("validate_ids=True synchronises every batch; use the default 'lazy' (checked in result())")
         self.model, self.dev = model, p.device
         self.B, self.F, self.depth, self.use_graph = batch_size, nfield, depth, use_graph
         self.copy_stream = torch.cuda.Stream(self.dev)
@@ -118,6 +119,9 @@ class BatchScorer:
             else:
                 y = self._forward(s)
             s.y_host.copy_(y, non_blocking=True)
+            flag = getattr(self.model, '_err_flag', None)
+            if flag is not None and getattr(self.model, 'validate_ids', False):
+                s.flag_host.copy_(flag, non_blocking=True)     # 4 bytes behind y: the id check costs no synchronisation
             s.ev_done.record(s.stream)
         s.used = True
         self.n_submitted += 1
@@ -130,6 +134,10 @@ class BatchScorer:
             raise ValueError('ticket is not outstanding')
         s = self.slots[ticket % self.depth]
         s.ev_done.synchronize()
+        if int(s.flag_host[0]) & 1:        # the reference raises IndexError for an id outside [0, nfeat) (layers.py:20)
+            s.flag_host.zero_()
+            self.model._err_flag.zero_()
+            raise IndexError('index out of range in self (armnet_b200: id outside [0, nfeat) in a scored batch)')
         return s.y_host
 
     def score(self, batches):

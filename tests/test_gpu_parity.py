@@ -238,6 +238,70 @@ def test_out_of_range_id_raises_index_error():
             m({'id': ids, 'value': torch.ones(4, 5, device=d)})
 
 
+@pytest.mark.parametrize('K,O,alpha', [(8, 128, 1.7), (4, 300, 2.0), (16, 128, 1.5)])
+def test_large_neuron_counts_run_in_row_chunks(K, O, alpha):
+    """--h x --nattn_head beyond what one CTA's shared memory holds (the reference accepts any size, train.py:24,28):
+    the forward runs in passes over chunks of K*O rows; same function, in-place clamp applied once, eval-mode arm_bn
+    epilogue per row."""
+    from armnet_b200 import ops
+    from oracle import armnet_oracle as oracle
+    d = dev()
+    torch.manual_seed(K * O)
+    B, F, E, V = 67, 39, 10, 4000
+    R = K * O
+    ids = torch.randint(0, V, (B, F))
+    values = torch.rand(B, F) * 1.2 - 0.1
+    table = torch.randn(V, E) * 0.6
+    W, Q, Vv = torch.randn(K, E, E) * 0.5, torch.randn(K, O, E) * 0.5, torch.randn(K, O, F)
+    st = {'embedding.embedding.weight': table, 'attn_layer.bilinear_w': W, 'attn_layer.query': Q,
+          'attn_layer.values': Vv}
+    ref = oracle.hot_path(st, alpha, ids, values.clone())
+    vals = values.clone().to(d)
+    post = (torch.randn(R, device=d) * 0.1 + 1, torch.rand(R, device=d) + 0.5, torch.randn(R, device=d))
+    z, _ = ops.fused_forward(ids.to(d), vals, table.to(d), W.to(d), Q.to(d), Vv.to(d), alpha)
+    assert ops.last_launch_count() >= 3                        # prepare + at least two row chunks
+    zb, _ = ops.fused_forward(ids.to(d), values.clone().to(d), table.to(d), W.to(d), Q.to(d), Vv.to(d), alpha, post=post)
+    torch.cuda.synchronize()
+    assert torch.equal(vals.cpu(), values.clamp(0.001, 1.0))
+    assert norm_rel(z.cpu(), ref['z']) <= TOL_NORM
+    zb_ref = (z - post[0][None, :, None]) * post[1][None, :, None] + post[2][None, :, None]
+    assert torch.allclose(zb, zb_ref, rtol=1e-6, atol=1e-6)
+    with pytest.raises(RuntimeError):                          # validation outputs need all rows in one pass
+        ops.fused_forward(ids.to(d), values.clone().to(d), table.to(d), W.to(d), Q.to(d), Vv.to(d), alpha, want_p=True)
+
+
+def test_out_of_range_id_lazy_check_and_scorer():
+    """Default validate_ids = 'lazy': no per-batch synchronisation, the kernels record the bad id in a device flag;
+    model.check_ids() and BatchScorer.result() raise the reference's IndexError (layers.py:20).  Rows with a bad id are
+    computed as zero embedding rows, the rest of the batch is unaffected."""
+    import armnet_b200 as ab
+    d = dev()
+    torch.manual_seed(0)
+    m = ab.ARMNetModel(39, 500, 10, 2, 1.7, 64, 1, 8, 0.0, False, 1, 8).to(d).eval()
+    assert m.validate_ids == 'lazy'
+    ids = torch.randint(0, 500, (64, 39), device=d)
+    vals = torch.ones(64, 39, device=d)
+    with torch.no_grad():
+        y0 = m({'id': ids, 'value': vals.clone()})
+        m.check_ids()                                  # clean
+        bad = ids.clone()
+        bad[5, 7] = 500
+        y1 = m({'id': bad, 'value': vals.clone()})     # does not raise here ...
+        with pytest.raises(IndexError):
+            m.check_ids()                              # ... but here
+        m.check_ids()                                  # flag was reset
+        keep = torch.arange(64, device=d) != 5
+        assert torch.equal(y0[keep], y1[keep])
+    scorer = ab.BatchScorer(m, 64, 39, depth=2, compute_streams=1)
+    t = scorer.submit(ids.cpu().pin_memory(), vals.cpu().pin_memory())
+    assert torch.allclose(scorer.result(t).to(d), y0, rtol=1e-6, atol=1e-6)
+    t = scorer.submit(bad.cpu().pin_memory(), vals.cpu().pin_memory())
+    with pytest.raises(IndexError):
+        scorer.result(t)
+    t = scorer.submit(ids.cpu().pin_memory(), vals.cpu().pin_memory())
+    assert torch.allclose(scorer.result(t).to(d), y0, rtol=1e-6, atol=1e-6)
+
+
 def test_bad_arguments_fail_loudly():
     from armnet_b200 import ops
     d = dev()

@@ -200,6 +200,8 @@ def run(epoch, model, split, args, plogger, dev, rank, world, optimizer=None, re
                          f'AUC {float(auc_avg.val):4f} ({auc_avg.avg:4f}) Loss {float(loss_avg.val):8.4f} ({loss_avg.avg:8.4f})')
         if bi >= args.eval_freq:
             break
+    if hasattr(model, 'check_ids'):
+        model.check_ids()            # the reference's IndexError for ids outside [0, nfeat), once per split (lazy flag)
     if rank == 0:
         plogger.info(f'{namespace}\tTime {time_avg.sum:10.1f}s AUC {auc_avg.avg:8.4f} Loss {loss_avg.avg:8.4f}')
     return auc_avg.avg
