@@ -494,8 +494,10 @@ def _check_tensor_core_case(alpha, F, scale, E):
             err = (ex[k].double() - ref64[k].reshape(shape)).abs().max().item()
             assert err <= bound[k], (key, k, err, bound[k], own[k])
         if 'z' in bound:
-            err = (z.double() - ref64['z'].reshape(B, R, E)).abs().max().item()
-            assert err <= bound['z'], (key, 'z', err, bound['z'], own['z'])
+            # z = exp(s): an error ds in s is an error z ds in z, so where |s| is large the bound on z follows s's
+            z64 = ref64['z'].reshape(B, R, E)
+            ok = (z.double() - z64).abs() <= torch.clamp(z64.abs() * (1.5 * bound['s']), min=bound['z'])
+            assert ok.all(), (key, 'z', (z.double() - z64).abs().max().item(), bound['z'], bound['s'], own['z'])
         assert (ex['p'].sum(-1) - 1).abs().max().item() < 1e-5, key
     zm, zf = outs['mma', True][0], outs['fp32', True][0]
     assert torch.equal(torch.isfinite(zm), torch.isfinite(zf))
