@@ -30,6 +30,8 @@ SIGNATURES = {
     'armnet_fused_workspace_bytes': (_Z, [_I, _I, _I, _I]),
     'armnet_fused_bwd_supported': (_I, [_I, _I]),
     'armnet_fused_fwd_kernel_kind': (_I, [_I, _I, _I, _I, _F, _I]),
+    'armnet_fused_bwd_finish_workspace_bytes': (_Z, [_I, _I, _I]),
+    'armnet_fused_bwd_finish_f32': (_I, [_P, _I, _P, _L, _L, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'armnet_fused_bwd_f32': (_I, [_P, _I, _P, _P, _L, _L, _P, _P, _P, _I, _F, _L, _I, _I, _I, _I, _I,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'armnet_mlp_split_weight_f32': (_I, [_P, _L, _P, _P, _P]),

@@ -10,7 +10,7 @@ import torch
 from . import _capi
 from ._capi import SOLVER_AUTO, SOLVER_BISECT, check, lib
 
-__all__ = ['fused_prepare', 'transpose2d', 'linear_tf32x3', 'linear_dense', 'linear_gather', 'batch_norm_train', 'clamp_adam', 'partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
+__all__ = ['fused_prepare', 'transpose2d', 'linear_tf32x3', 'linear_dense', 'linear_gather', 'batch_norm_train', 'clamp_adam', 'partials_to_dense', 'mlp_split_weight', 'mlp_first_linear', 'mlp_tail', 'mlp_pack_tail', 'embed_gather', 'entmax', 'fused_forward', 'fused_backward', 'fused_backward_finish', 'fused_interaction', 'fused_bwd_supported', 'new_error_flag', 'raise_if_bad_ids',
            'SOLVER_AUTO', 'SOLVER_BISECT', 'last_launch_count']
 
 
@@ -291,6 +291,33 @@ def fused_backward(ids, values, table, bilinear_w, query, att_values, alpha, z, 
     return w, dg, dvals, dm
 
 
+def fused_backward_finish(ids, values, V, bilinear_w, query, w, dg, z, dz, dm, one_head=False, dT=None):
+    """armnet_fused_bwd_finish_f32: (dT [V,E], dW, dQ) from the partials of fused_backward; see include/armnet_b200.h.
+    dT: optional [V,E] tensor to accumulate into (zeroed here when not given)."""
+    _need_cuda(ids, values, bilinear_w, query, w, dg, z, dz, dm)
+    ids_c = ids.contiguous()
+    values = _f32c(values, 'values')
+    W, Q = _f32c(bilinear_w.detach(), 'bilinear_w'), _f32c(query.detach(), 'query')
+    w, dg, z, dz, dm = (_f32c(t, n) for t, n in ((w, 'w'), (dg, 'dg'), (z, 'z'), (dz, 'dz'), (dm, 'dm')))
+    B, F = ids_c.shape
+    if one_head:
+        D, K, O = W.shape[0], 1, Q.shape[0]
+        E = W.shape[1]
+    else:
+        K, O, D = Q.shape
+        E = W.shape[1]
+    dev = w.device
+    if dT is None:
+        dT = torch.zeros(V, E, dtype=torch.float32, device=dev)
+    dW, dQ = torch.empty_like(W), torch.empty_like(Q)
+    ws = torch.empty(max(lib.armnet_fused_bwd_finish_workspace_bytes(E, K, O) // 4, 4), dtype=torch.float32, device=dev)
+    check(lib.armnet_fused_bwd_finish_f32(ids_c.data_ptr(), _ids_arg(ids_c), values.data_ptr(), V, B, F, E, D, K, O,
+                                          W.data_ptr(), Q.data_ptr(), int(one_head), w.data_ptr(), dg.data_ptr(),
+                                          z.data_ptr(), dz.data_ptr(), dm.data_ptr(), dT.data_ptr(), dW.data_ptr(),
+                                          dQ.data_ptr(), ws.data_ptr(), _stream()), 'armnet_fused_bwd_finish_f32')
+    return dT, dW, dQ
+
+
 class _FusedInteractionFn(torch.autograd.Function):
     """z = exp(sum_f entmax(g)_f V_f e_f) with the fused forward and backward kernels; gradients for the embedding
     table (dense, like nn.Embedding(sparse=False)), bilinear_w, query and values. ids / values get none
@@ -310,27 +337,13 @@ class _FusedInteractionFn(torch.autograd.Function):
         one_head = ctx.one_head
         w, dg, dvals, dm = fused_backward(ids, values, table, W, Q, Vv, ctx.alpha, z, dz.contiguous(), tau,
                                           one_head=one_head)
-        B, F = ids.shape
-        V, E = table.shape
-        D = W.shape[0] if one_head else W.shape[2]
-        scale = D ** -0.5
-        ds = dz * z                                                                 # [B,R,E]
-        if one_head:
-            Mt = torch.einsum('dx,od->ox', W, Q) * scale                            # [R,E]: scale * M[x][r]
-        else:
-            Mt = (torch.einsum('kxy,koy->kox', W, Q) * scale).reshape(-1, E)
-        de = torch.bmm(w, ds) + torch.matmul(dg, Mt)                                # [B,F,E]
-        dT = torch.zeros(V, E, dtype=table.dtype, device=table.device)
-        dT.index_add_(0, ids.reshape(-1).long(), (de * values.unsqueeze(2)).reshape(-1, E))
-        dms = dm * scale                                                            # [R,E]
-        if one_head:
-            dW = torch.einsum('ox,od->dx', dms, Q)
-            dQ = torch.einsum('ox,dx->od', dms, W)
-        else:
-            dmk = dms.reshape(Q.shape[0], Q.shape[1], E)
-            dW = torch.einsum('kox,koy->kxy', dmk, Q)
-            dQ = torch.einsum('kox,kxy->koy', dmk, W)
-        return dT, dW, dQ, dvals.reshape(Vv.shape), None, None, None, None, None
+        # FlatAdam points table.grad at its slice of the flat gradient bucket (zeroed every step): scatter straight into
+        # it instead of materialising a second [V,E] tensor that autograd would add to it (64 MB at config 4)
+        g = table.grad if getattr(table, '_armnet_flat_grad', False) else None
+        inplace = g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.shape == table.shape
+        dT, dW, dQ = fused_backward_finish(ids, values, table.shape[0], W, Q, w, dg, z, dz.contiguous(), dm,
+                                           one_head=one_head, dT=g if inplace else None)
+        return (None if inplace else dT), dW, dQ, dvals.reshape(Vv.shape), None, None, None, None, None
 
 
 def fused_interaction(table, bilinear_w, query, att_values, ids, values, alpha, one_head=False, solver=SOLVER_AUTO):

@@ -94,6 +94,7 @@ class FlatAdam:
                 view.copy_(p)
                 p.data = view
                 p.grad = self.flat_g[off:off + p.numel()].view_as(p)
+                p._armnet_flat_grad = True      # kernels may accumulate straight into p.grad (ops._FusedInteractionFn)
                 off += sz
 
     def numel(self):

@@ -141,7 +141,7 @@ int armnet_fused_fwd_prepared_f32(const void *ids, int ids_i32, float *values, c
  * (row index fastest: coalesced, and the layout a batched GEMM over rows wants), and accumulates over the batch
  *     acc_dvalues [K*O,F] += p * (ds . e)                      gradient of att_values
  *     acc_dm      [K*O,E] += sum_f dg_f * e_f                  gradient of the pre-contracted matrix, unscaled
- * with ds = dz * z.  The caller zeroes the accumulators, and finishes with dense products (host side, cuBLAS):
+ * with ds = dz * z.  The caller zeroes the accumulators; armnet_fused_bwd_finish_f32 (below) turns the partials into
  *     de[b,f,:] = sum_r out_w[b,f,r] ds[b,r,:] + d_k^-0.5 sum_r out_dg[b,f,r] M[:,r],   dT[id] += de * value,
  *     dW, dQ from acc_dm.   z: forward output WITHOUT the arm_bn epilogue; values: already clamped by the forward.
  * armnet_fused_bwd_supported() tells whether a backward kernel instance exists for (F, E).
@@ -163,6 +163,22 @@ int armnet_fused_bwd_f32(const void *ids, int ids_i32, float *values, const floa
                          int w_is_linear_layout, float alpha, int64_t B, int F, int E, int D, int K, int O,
                          const float *z, const float *dz, const float *tau, float *out_w, float *out_dg,
                          float *acc_dvalues, float *acc_dm, void *workspace, int *err_flag, void *stream);
+
+/*
+ * Finishes the fused backward on the package's own kernels: from the partials of armnet_fused_bwd_f32 to the parameter
+ * gradients the reference's autograd produces for the hot path (models/layers.py:12,20-21 dense embedding gradient;
+ * models/armnet.py:33-34 einsum backward; models/armnet_1h.py:30-32):
+ *     de[b,f,:]      = sum_r out_w[b,f,r] (dz*z)[b,r,:] + d_k^-0.5 sum_r out_dg[b,f,r] M[:,r]   (mma.sync 3xTF32, one CTA per sample)
+ *     dT[ids[b,f],:] += de[b,f,:] * values[b,f]            dT [V,E]: the caller zeroes it (or accumulates across micro-batches)
+ *     dW, dQ         = the two contractions of acc_dm with query / bilinear_w, times d_k^-0.5 (written, not accumulated)
+ * bilinear_w / query in the layouts of armnet_fused_fwd_f32 (w_is_linear_layout: nn.Linear weight [D,E], K = 1).
+ * workspace: armnet_fused_bwd_finish_workspace_bytes(E, K, O) bytes, 16-byte aligned.  F <= 64.
+ */
+size_t armnet_fused_bwd_finish_workspace_bytes(int E, int K, int O);
+int armnet_fused_bwd_finish_f32(const void *ids, int ids_i32, const float *values, int64_t V, int64_t B, int F, int E,
+                                int D, int K, int O, const float *bilinear_w, const float *query, int w_is_linear_layout,
+                                const float *w, const float *dg, const float *z, const float *dz, const float *acc_dm,
+                                float *dT, float *dW, float *dQ, void *workspace, void *stream);
 
 /*
  * The trailing dense MLP in eval mode (models/layers.py:68-88, called at models/armnet.py:92, armnet_1h.py:89):
