@@ -334,6 +334,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
