@@ -4,7 +4,7 @@
 //
 // Same function and the same C ABI entry as armnet_fwd_kernel (fused_fwd.cuh); what changes is who computes the logits
 //   X[b, r, f] = sum_x M'[x, r] e[b, f, x]       (armnet.py:33-34 with entmax.py:42's (alpha-1) folded into M'),
-// half of the FP32-pipe work of armnet_fwd_kernel.  Here they are a tcgen05.mma.kind::tf32 per (256 neurons, 2 samples):
+// half of the FP32-pipe work of armnet_fwd_kernel.  Here they are a tcgen05.mma.kind::tf32 per (128 neurons, 2 samples):
 //   * A = rows of M'^T (M = 128 neurons per MMA), resident in TMEM for the whole kernel (written once with tcgen05.st);
 //     B = the gathered embedding rows of a TILE of two samples (N = 2 x 40 rows), in shared memory, K-major, 128-byte
 //     swizzle; D (128 lanes x 80 columns fp32) in TMEM.  Four K = 8 steps cover a "packed 3xTF32" K axis of 32:
@@ -12,24 +12,24 @@
 //     with m = M - trunc_tf32(M), l = e - trunc_tf32(e): the tensor core reads the top 19 bits of an fp32 operand, so
 //     sum_k A_k B_k = sum_x (M e + M l + m e) -- fp32-grade logits (5.6e-7 norm-relative on B200,
 //     tools/ubench/tmem_logits_check.cu) from ONE accumulation chain of 4 MMAs (~45 cycles each).
-//   * TMEM lane i of the D block of A-block (2h + j) is neuron 256h + 64(i/32) + 2(i%32) + j, so a thread that reads its
-//     lane from the two blocks of an item (h) gets the two ADJACENT rows (2l, 2l+1) of the same sample as 2 x 40
-//     registers, fields packed in (f, f+1) pairs -- the layout entmax_rows.cuh works on.  The D slot is released as soon
-//     as the registers are loaded (two slots: the MMAs of the next item run under the current item's entmax).
+//   * TMEM lane i of the D block of A-block kb is neuron 128 kb + i, so a thread reads ITS row's 40 logits with
+//     tcgen05.ld (fields packed in (f, f+1) register pairs -- the layout entmax_rows.cuh works on) and the D slot is
+//     released as soon as the registers are loaded (four slots: the MMAs of the next items run under the current entmax).
+//     NR = 2 (opt-in): a thread owns the same lane of two A blocks, see the kernel template.
 //   * Everything after the logits is thread-private like in armnet_fwd_kernel: entmax (entmax_rows.cuh: MUFU-free
 //     pre-solve, q-norm Newton, last sweep fused with the cross product), s[x] = sum_f p_f V_f e[f,x] on FFMA2 with the
 //     e rows read (warp-broadcast) from the B tile itself -- its first 10 floats are the exact fp32 e --, exp, optional
-//     eval-mode arm_bn, one TMA bulk store per warp-unit (64 consecutive neurons x E of one sample).
+//     eval-mode arm_bn, one TMA bulk store per warp-unit (32 consecutive neurons x E of one sample).
 // Roles: 16 consumer warps (4 per TMEM lane quadrant; units = (item, quadrant, sample) taken in order from one counter
 // per quadrant) + three producer warps that only meet through mbarriers: the GATHER warp prefetches ids / values (clamp
 // in place, range check) and issues the TMA bulk row gathers up to 16 tiles ahead into a raw ring; the CONVERT warp turns
 // landed rows into B-tile rows (scale by the value: e = T[id] v exactly as layers.py:21; split; swizzled store); the MMA
 // warp issues the tcgen05.mma of an item the moment its tile is converted and a D slot is free (a single producer warp
-// doing all three in sequence starved the consumers: 28 % issue utilisation, profiles/r2_v1_*).  No CTA-wide barrier in
-// steady state.
+// doing all three in sequence starved the consumers: 28 % issue utilisation, profiles/r2_v3_summary.md).  No CTA-wide
+// barrier in steady state; every mbarrier wait is bounded (a protocol bug traps instead of hanging the device).
 // Requirements (host-checked, everything else runs on armnet_fwd_kernel): F in {2NP-1, 2NP} for a compiled NP, E <= 10,
-// K*O a multiple of 256 and <= 768, 16-byte-aligned table rows (the module's padded shadow table), no debug outputs,
-// solver != literal bisection.
+// K*O a multiple of 128 and <= 768 (tensor-memory columns), 16-byte-aligned table rows (the module's padded shadow
+// table), no validation outputs, solver != literal bisection.
 #pragma once
 
 #include "entmax_rows.cuh"
