@@ -162,6 +162,7 @@ int tmem_launch(const char *who, const void *ids, int ids_i32, float *values, co
         return ARMNET_ERR_UNSUPPORTED;
     }
     const TmemSmem L(I->NP, NR, P);
+    P.inv_ipt = (unsigned)((0x100000000ull + (unsigned)(R / 128 / NR) - 1) / (unsigned)(R / 128 / NR));
     const void *kernel = NR == 2 ? I->kernel2 : I->kernel;
     const unsigned grid = (unsigned)(P.n_tiles < di.sm_count ? P.n_tiles : di.sm_count);
     ARMNET_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
@@ -171,3 +172,10 @@ int tmem_launch(const char *who, const void *ids, int ids_i32, float *values, co
 }
 
 }  // namespace armnet
+
+#ifdef ARMNET_TMEM_TRACE
+// tuning builds only: copy the timeline trace of the last launch (148 CTAs x 64 clock64() slots) to the host
+extern "C" int armnet_debug_tmem_trace(long long *out) {
+    return (int)cudaMemcpyFromSymbol(out, armnet::g_tm_trace, sizeof(long long) * 148 * 64);
+}
+#endif

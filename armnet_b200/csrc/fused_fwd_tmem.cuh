@@ -57,6 +57,29 @@ constexpr int kTmTiles = 4;                           // B-tile ring (tiles of 2
 constexpr int kTmKP = 32;                             // packed K (floats per operand row = 128 bytes)
 constexpr int kTmEL = 10;                             // embedding lanes of the packed layout
 
+// Timeline trace (tuning builds only, -DARMNET_TMEM_TRACE): clock64() of CTA-local events, 64 slots per CTA.
+#ifdef ARMNET_TMEM_TRACE
+__device__ long long g_tm_trace[148 * 64];
+#define TM_TRACE(slot)                                                                        \
+    do {                                                                                      \
+        if ((threadIdx.x & 31) == 0 && blockIdx.x < 148) g_tm_trace[blockIdx.x * 64 + (slot)] = clock64(); \
+    } while (0)
+#define TM_TRACE_ONCE(slot, cond)                                                             \
+    do {                                                                                      \
+        if (cond) TM_TRACE(slot);                                                             \
+    } while (0)
+#else
+#define TM_TRACE(slot) do { } while (0)
+#define TM_TRACE_ONCE(slot, cond) do { } while (0)
+#endif
+
+#ifndef ARMNET_TM_ABLK
+#define ARMNET_TM_ABLK 1       // A operand published block by block (0: one arrival after all blocks)
+#endif
+#ifndef ARMNET_TM_UMULHI
+#define ARMNET_TM_UMULHI 1     // item -> tile index by multiply-high instead of a runtime division
+#endif
+
 struct TmemParams {
     const void *ids;
     float *values;
@@ -79,6 +102,7 @@ struct TmemParams {
     int look;        // tiles of gather look-ahead
     int row_bytes;   // bytes fetched per embedding row (multiple of 16)
     int tma_store;
+    unsigned inv_ipt;   // ceil(2^32 / items per tile): item -> tile index by __umulhi
 };
 
 // Shared-memory carve-up, identical on host (sizing) and device (pointers). Offsets in bytes.
@@ -195,14 +219,14 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
     unsigned char *smem = smem_tm;
     const TmemSmem L(NP, NR, P);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.off_bar);
-    uint64_t *bar_par = bar;                        // V table landed
+    uint64_t *v_ready = bar;                        // V table landed
     uint64_t *d_full = bar + 1;                     // [4]  MMAs of an item done (tcgen05.commit)
     uint64_t *d_empty = bar + 5;                    // [4]  all 8 units of an item hold their logits in registers
     uint64_t *tile_full = bar + 9;                  // [kTmTiles]  tile converted (e rows visible to the consumers)
     uint64_t *tile_empty = tile_full + kTmTiles;    // [kTmTiles]  every unit of the tile is done reading e
     uint64_t *raw_full = tile_empty + kTmTiles;     // [n_raw <= 32]  gathered rows of a sample landed
     uint64_t *raw_empty = raw_full + 32;            // [n_raw <= 32]  the convert warp is done with the sample's raw rows
-    uint64_t *a_ready = raw_empty + 32;             // the A operand (M'^T) sits in tensor memory
+    uint64_t *a_ready = bar + 90;                   // [NBLK <= 8]  A block kb (128 rows of M'^T) sits in tensor memory
     int *next_unit = reinterpret_cast<int *>(smem + L.off_bar + 960);   // [4] one counter per lane quadrant
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.off_bar + 992);
     unsigned char *tiles = smem + L.off_tiles;
@@ -219,10 +243,14 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
     const int G = (int)gridDim.x;
     const int n_local = (P.n_tiles - (int)blockIdx.x + G - 1) / G;   // tiles blockIdx.x + t * G
     const EntmaxParams ep = P.ep;
+    TM_TRACE_ONCE(0, warp == 0);
+
+    const int rows_tile = 2 * F;          // ids / values of a tile are contiguous in the [B, F] arrays
+    constexpr int KR = (2 * NFP + 31) / 32;
 
     if (tid == 0) {
-        mbar_init(bar_par, 1);
-        mbar_init(a_ready, 4);
+        mbar_init(v_ready, 1);
+        for (int kb = 0; kb < NBLK; ++kb) mbar_init(&a_ready[kb], 4);
         for (int s = 0; s < NSLOT; ++s) {
             mbar_init(&d_full[s], 1);
             mbar_init(&d_empty[s], 8);
@@ -237,8 +265,8 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
         }
         for (int qd = 0; qd < 4; ++qd) next_unit[qd] = 0;
         mbar_fence_init();
-        mbar_arrive_expect_tx(bar_par, (uint32_t)L.v_bytes);
-        tma_load_bulk(smem + L.off_V, P.Vpk, (uint32_t)L.v_bytes, bar_par);
+        mbar_arrive_expect_tx(v_ready, (uint32_t)L.v_bytes);
+        tma_load_bulk(smem + L.off_V, P.Vpk, (uint32_t)L.v_bytes, v_ready);
     }
     if (warp == kTmWarpMma) tm_alloc(tmem_slot, 512);
     // B tiles start as zeros: the pad rows (field NFP-1 for odd F, samples past the batch) and the two pad floats of
@@ -249,23 +277,45 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
     tm_fence_before();
     __syncthreads();
     tm_fence_after();
+    TM_TRACE_ONCE(1, warp == 0);
     const uint32_t tmem = *tmem_slot;
-    // A operand: TMEM columns [0, A_COLS), lane i of block kb = packed row (kb, i)
+    // A operand: TMEM columns [0, A_COLS), lane i of block kb = packed row (kb, i).  Block kb + 1 is in flight (registers)
+    // while block kb is stored and published: the first MMA only needs block 0.
     if (warp < 4) {
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-        for (int kb = 0; kb < NBLK; ++kb) {
+        float4 cur[8], nxt[8];
+        auto load_block = [&](float4 (&dst)[8], int kb) {
             const float4 *src = reinterpret_cast<const float4 *>(P.Apk + ((long long)kb * 128 + warp * 32 + lane) * kTmKP);
 #pragma unroll
+            for (int c = 0; c < 8; ++c) dst[c] = __ldg(src + c);
+        };
+        load_block(cur, 0);
+        for (int kb = 0; kb < NBLK; ++kb) {
+            if (kb + 1 < NBLK) load_block(nxt, kb + 1);
+#pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
-                const float4 a = __ldg(src + 2 * c8), b = __ldg(src + 2 * c8 + 1);
+                const float4 a = cur[2 * c8], b = cur[2 * c8 + 1];
                 const float r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 tm_st8(taddr + (uint32_t)(kb * kTmKP + c8 * 8), r);
             }
+#if ARMNET_TM_ABLK
+            tm_st_wait();
+            tm_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_ready[kb]);   // only the MMA warp waits for it, block by block
+            TM_TRACE_ONCE(2, warp == 0 && kb == 0);
+#endif
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
         }
+#if !ARMNET_TM_ABLK
         tm_st_wait();
         tm_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready);   // only the MMA warp waits for it: gathers and conversions start at once
+        if (lane == 0)
+            for (int kb = 0; kb < NBLK; ++kb) mbar_arrive(&a_ready[kb]);
+        TM_TRACE_ONCE(2, warp == 0);
+#endif
     }
     const uint32_t d_base = tmem + (uint32_t)A_COLS;
 
@@ -277,25 +327,38 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
     }
 #endif
     auto sample_valid = [&](int t, int s) { return 2 * ((long long)blockIdx.x + (long long)t * G) + s < P.B; };
-    const int rows_tile = 2 * F;          // ids / values of a tile are contiguous in the [B, F] arrays
-    constexpr int KR = (2 * NFP + 31) / 32;
 
     if (warp == kTmWarpGather) {
         // =========================================================== gather warp: ids / values -> TMA bulk row gathers
-        long long pid[KR];                    // prefetched ids / clamped values of the next tile to gather
+        // `prefetch` only ISSUES the loads of a tile's ids / values (one tile ahead); `finish` clamps / range-checks at use
+        long long pid[KR];
         float pv[KR];
         auto prefetch = [&](int t) {
             const long long row0 = ((long long)blockIdx.x + (long long)t * G) * rows_tile;
 #pragma unroll
             for (int k = 0; k < KR; ++k) {
                 const int idx = lane + 32 * k;
+                const long long row = row0 + idx;
                 long long id = 0;
                 float v = 0.f;
-                const long long row = row0 + idx;
                 if (idx < rows_tile && t < n_local && row < P.B * F) {
-                    id = P.ids_i32 ? (long long)reinterpret_cast<const int *>(P.ids)[row]
-                                   : reinterpret_cast<const long long *>(P.ids)[row];
+                    id = P.ids_i32 ? (long long)__ldg(reinterpret_cast<const int *>(P.ids) + row)
+                                   : __ldg(reinterpret_cast<const long long *>(P.ids) + row);
                     v = P.values[row];
+                }
+                pid[k] = id;
+                pv[k] = v;
+            }
+        };
+        auto finish = [&](int t) {
+            const long long row0 = ((long long)blockIdx.x + (long long)t * G) * rows_tile;
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                const int idx = lane + 32 * k;
+                const long long row = row0 + idx;
+                long long id = pid[k];
+                float v = pv[k];
+                if (idx < rows_tile && t < n_local && row < P.B * F) {
                     if (P.clamp) {  // armnet.py:82 -- in place on the caller's tensor
                         const float vc = fminf(fmaxf(v, P.clamp_lo), P.clamp_hi);
                         if (P.clamp_inplace && vc != v) P.values[row] = vc;
@@ -312,55 +375,67 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
             }
         };
         prefetch(0);
+        TM_TRACE(53);
+        int rs0 = 0, use = 0;   // raw-ring slot of the tile's first sample (n_raw is even: 2 t % n_raw) and its lap, no division
         for (int t = 0; t < n_local; ++t) {
+            finish(t);
             // raw slots of tile t were last used by tile t - look: wait until the convert warp has read them
-            if (lane < 2 && sample_valid(t, lane)) {
-                const int ls = 2 * t + lane, rs = ls % P.n_raw, use = ls / P.n_raw;
-                if (use > 0) tm_wait(&raw_empty[rs], (uint32_t)(use - 1) & 1u);
-            }
+            if (lane < 2 && sample_valid(t, lane) && use > 0) tm_wait(&raw_empty[rs0 + lane], (uint32_t)(use - 1) & 1u);
             __syncwarp();
+            TM_TRACE_ONCE(55, t == 0);
 #pragma unroll
             for (int k = 0; k < KR; ++k) {   // the values first: they are published by the arrive below
                 const int idx = lane + 32 * k;
                 if (idx < rows_tile) {
                     const int s = idx >= F ? 1 : 0, f = idx - s * F;
-                    if (sample_valid(t, s)) vals[((2 * t + s) % P.n_raw) * L.fpad + f] = pv[k];
+                    if (sample_valid(t, s)) vals[(rs0 + s) * L.fpad + f] = pv[k];
                 }
             }
             __syncwarp();
+            TM_TRACE_ONCE(56, t == 0);
             if (lane < 2 && sample_valid(t, lane))
-                mbar_arrive_expect_tx(&raw_full[(2 * t + lane) % P.n_raw], (uint32_t)(F * P.row_bytes));
+                mbar_arrive_expect_tx(&raw_full[rs0 + lane], (uint32_t)(F * P.row_bytes));
             __syncwarp();
+            TM_TRACE_ONCE(57, t == 0);
 #pragma unroll
             for (int k = 0; k < KR; ++k) {
                 const int idx = lane + 32 * k;
                 if (idx < rows_tile) {
                     const int s = idx >= F ? 1 : 0, f = idx - s * F;
                     if (sample_valid(t, s)) {
-                        const int rs = (2 * t + s) % P.n_raw;
+                        const int rs = rs0 + s;
                         tma_load_bulk(raw + rs * L.raw_sample_bytes + f * P.row_bytes, P.table + pid[k] * P.ld,
                                       (uint32_t)P.row_bytes, &raw_full[rs]);
                     }
                 }
             }
+            TM_TRACE_ONCE(3, t == 0);
             prefetch(t + 1);
+            rs0 += 2;
+            if (rs0 >= P.n_raw) {
+                rs0 = 0;
+                ++use;
+            }
         }
+        TM_TRACE(12);
     } else if (warp == kTmWarpConvert) {
         // =========================================================== convert warp
         // landed rows of tile t -> B tile: e = row * v (layers.py:21), packed [e | lo(e) | e | 0 0], 128-byte swizzle
+        int rs0 = 0, use = 0;   // as in the gather warp
         for (int t = 0; t < n_local; ++t) {
             const int bt = t % kTmTiles;
             if (t >= kTmTiles) tm_wait(&tile_empty[bt], (uint32_t)(t / kTmTiles - 1) & 1u);
             for (int s = 0; s < 2; ++s)
-                if (sample_valid(t, s)) tm_wait(&raw_full[(2 * t + s) % P.n_raw], (uint32_t)((2 * t + s) / P.n_raw) & 1u);
+                if (sample_valid(t, s)) tm_wait(&raw_full[rs0 + s], (uint32_t)use & 1u);
             unsigned char *tile = tiles + bt * L.tile_bytes;
+            TM_TRACE_ONCE(4, t == 0);
 #pragma unroll
             for (int k = 0; k < KR; ++k) {
                 const int idx = lane + 32 * k;
                 if (idx < rows_tile) {
                     const int s = idx >= F ? 1 : 0, f = idx - s * F;
                     if (sample_valid(t, s)) {
-                        const int rs = (2 * t + s) % P.n_raw;
+                        const int rs = rs0 + s;
                         const float4 *src = reinterpret_cast<const float4 *>(raw + rs * L.raw_sample_bytes + f * P.row_bytes);
                         const float v = vals[rs * L.fpad + f];
                         float e[12], l[12];
@@ -395,13 +470,18 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
             fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&tile_full[bt]);
-            if (lane < 2 && sample_valid(t, lane)) mbar_arrive(&raw_empty[(2 * t + lane) % P.n_raw]);
+            if (lane < 2 && sample_valid(t, lane)) mbar_arrive(&raw_empty[rs0 + lane]);
+            TM_TRACE_ONCE(5, t == 0);
+            rs0 += 2;
+            if (rs0 >= P.n_raw) {
+                rs0 = 0;
+                ++use;
+            }
         }
+        TM_TRACE(13);
     } else if (warp == kTmWarpMma) {
         // =========================================================== MMA warp: one elected lane issues tcgen05.mma
         const uint32_t idesc = tm_idesc_tf32(128, 2 * NFP);
-        tm_wait(a_ready, 0);
-        tm_fence_after();
         for (int t = 0; t < n_local; ++t) {
             const int bt = t % kTmTiles;
             tm_wait(&tile_full[bt], (uint32_t)(t / kTmTiles) & 1u);
@@ -409,7 +489,10 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
             for (int h = 0; h < IPT; ++h) {
                 const int i = t * IPT + h, slot = i % NSLOT;
                 if (i >= NSLOT) tm_wait(&d_empty[slot], (uint32_t)(i / NSLOT - 1) & 1u);
+                if (t == 0)
+                    for (int j = 0; j < NR; ++j) tm_wait(&a_ready[h * NR + j], 0);
                 tm_fence_after();
+                TM_TRACE_ONCE(6, i == 0);
                 if (lane == 0) {
                     const uint32_t d = d_base + (uint32_t)(slot * DSLOT);
 #pragma unroll
@@ -421,8 +504,10 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
                     tm_commit(&d_full[slot]);
                 }
                 __syncwarp();
+                TM_TRACE_ONCE(7, i == 0);
             }
         }
+        TM_TRACE(14);
     } else if (warp > kTmWarpMma) {
         // idle warp of the producer warpgroup
     } else {
@@ -431,20 +516,28 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
         const int n_units = n_local * IPT * 2;
         float *ost_warp = outs + warp * L.out_floats;
         int obuf = 0;
-        tm_wait(bar_par, 0);
+        tm_wait(v_ready, 0);
+#if ARMNET_TM_UMULHI
+#define TM_DIV_IPT(i) ((int)__umulhi((uint32_t)(i), P.inv_ipt))   // host-computed ceil(2^32 / IPT): no division, no register
+#else
+#define TM_DIV_IPT(i) ((i) / IPT)
+#endif
         int u_next = 0;
+        bool first_unit = true;
+        (void)first_unit;
         if (lane == 0) u_next = atomicAdd(&next_unit[qd], 1);
         if constexpr (NR == 2) {
         for (;;) {
             const int u = __shfl_sync(0xffffffffu, u_next, 0);
             if (u >= n_units) break;
             const int i = u >> 1, s = u & 1;       // item, sample inside the tile
-            const int t = i / IPT, h = i - t * IPT;
+            const int t = TM_DIV_IPT(i), h = i - t * IPT;
             const int slot = i % NSLOT;
             const int bt = t % kTmTiles;
             const long long b = 2 * ((long long)blockIdx.x + (long long)t * G) + s;
             const bool valid = b < P.B;
             const int r0 = h * 256 + qd * 32 + lane;   // this lane's two neurons: r0 and r0 + 128
+
             tm_wait(&d_full[slot], (uint32_t)(i / NSLOT) & 1u);
             tm_fence_after();
             if (lane == 0) u_next = atomicAdd(&next_unit[qd], 1);   // claim the next unit: the latency hides under this one
@@ -596,7 +689,7 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
             const int u = __shfl_sync(0xffffffffu, u_next, 0);
             if (u >= n_units) break;
             const int i = u >> 1, s = u & 1;       // item, sample inside the tile
-            const int t = i / NBLK, kb = i - t * NBLK;
+            const int t = TM_DIV_IPT(i), kb = i - t * NBLK;   // NR == 1: IPT == NBLK
             const int slot = i % NSLOT;
             const int bt = t % kTmTiles;
             const long long b = 2 * ((long long)blockIdx.x + (long long)t * G) + s;
@@ -607,6 +700,8 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
             float2 X[1][NP];
             tm_wait(&d_full[slot], (uint32_t)(i / NSLOT) & 1u);
             tm_fence_after();
+            TM_TRACE_ONCE(36 + warp, first_unit);
+            first_unit = false;
             {
                 const uint32_t tn = d_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(slot * DSLOT + s * NFP);
                 if (NP >= 16) tm_ld32(tn, &X[0][0]);
@@ -622,6 +717,7 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
             }
             if (ODD) X[0][NP - 1].y = neg_inf();
             tm_wait(&tile_full[bt], (uint32_t)(t / kTmTiles) & 1u);
+
 
             float2 acc[EL / 2];
             float tau[1], S[1] = {1.f};
@@ -656,6 +752,7 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
                 };
                 rows_entmax_cross<1, NP, ODD>(X, ep, tau, S, vrow, cross, reset);
             }
+            TM_TRACE_ONCE(10, warp == 0 && u == 0);
             // every lane is done reading the tile: hand it back (one arrival per unit)
             __syncwarp();
             if (lane == 0) mbar_arrive(&tile_empty[bt]);
@@ -708,10 +805,12 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
             }
         }
         }
+        TM_TRACE(16 + warp);
         if (P.tma_store && lane == 0) tma_store_wait_all<0>();
     }
     tm_fence_before();
     __syncthreads();
+    TM_TRACE_ONCE(15, warp == 0);
     if (warp == kTmWarpMma) tm_dealloc(tmem, 512);
 }
 
