@@ -39,6 +39,7 @@ SIGNATURES = {
     'armnet_mlp_linear_tf32x3': (_I, [_P, _L, _I, _P, _P, _I, _I, _P, _P]),
     'armnet_linear_tf32x3_dense': (_I, [_P, _L, _I, _P, _P, _I, _P, _P, _P]),
     'armnet_transpose_f32': (_I, [_P, _L, _L, _P, _P]),
+    'armnet_mlp_hidden_tc_f32': (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P]),
     'armnet_mlp_tail_packed_floats': (_Z, [_I, _I, _I]),
     'armnet_mlp_tail_f32': (_I, [_P, _I, _L, _I, _I, _I, _P, _P, _P]),
     'armnet_bn_workspace_floats': (_Z, [_L, _I, _I]),

@@ -701,6 +701,235 @@ __global__ void __launch_bounds__(T_THREADS, 1) mlp_tail_kernel(const TailParams
     }
 }
 
+// ------------------------------------------------------------------ a hidden layer after the first, on the tensor cores
+// One launch = one hidden Linear(H_in -> H_out <= 256) of layers.py:73-77 in eval mode, for 128 samples per CTA:
+//   x[m][k]  = relu(sum_s in[s][m/32][k][m%32] * a_in[k] + c_in[k])      the previous layer's activation, built by the
+//                                                                         producer warps straight into the swizzled A tile
+//   acc[m][n] = sum_k x[m][k] w[n][k]                                     tcgen05.mma kind::tf32, 3xTF32 like the first GEMM
+//   final:     y[m][o] = sum_n relu(acc[m][n] a_out[n] + c_out[n]) wf[o][n] + bf[o]      (this layer's BN/ReLU + layers.py:81)
+//   otherwise: out[0][m/32][n][m%32] = acc[m][n]                          (the next launch applies a_out / c_out)
+// so "split-K sums of layer 1 -> y" is ONE kernel on ceil(B/128) SMs (10 us at B = 4096) instead of the CUDA-core tail
+// kernel on B/32 SMs (27 us).  Roles as in mlp_gemm_tf32x3_kernel: warp 0 = TMA producer of the W tiles, warp 1 = TMEM owner
+// + MMA issuer, warps 2-5 = producers of the A tile (thread = sample row: coalesced reads along the sample axis of the
+// partial-sum layout) and epilogue (thread = TMEM lane = sample).
+constexpr int HT_MAX_NO = 4;
+struct HiddenParams {
+    const float *in;        // [in_splits][MB][H_in][32]
+    const float *a_in, *c_in;
+    const float *a_out, *c_out, *wf, *bf;   // final mode (y != null)
+    float *y;               // [B][NO]
+    float *out;             // [1][MB][H_out][32] when y == null
+    long long B;
+    int MB, in_splits, H_in, H_out, NO, kb_total;
+};
+
+constexpr int HT_THREADS = 64 + 2 * G_CONV_THREADS;   // TMA warp, MMA warp, 8 producer / epilogue warps
+__global__ void __launch_bounds__(HT_THREADS, 1)
+    mlp_hidden_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+                         const HiddenParams P) {
+    extern __shared__ __align__(1024) unsigned char smem_hid[];   // SWIZZLE_128B tiles need 1024-byte alignment
+    unsigned char *smem = smem_hid;
+    auto s_xh = [&](int s) { return smem + s * G_STAGE_BYTES; };
+    auto s_xl = [&](int s) { return smem + s * G_STAGE_BYTES + G_A_BYTES; };
+    auto s_wh = [&](int s) { return smem + s * G_STAGE_BYTES + 2 * G_A_BYTES; };
+    auto s_wl = [&](int s) { return smem + s * G_STAGE_BYTES + 2 * G_A_BYTES + G_B_BYTES; };
+    uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem + G_STAGES * G_STAGE_BYTES);   // W tiles landed (TMA)
+    uint64_t *bar_a = bar_w + G_STAGES;                                                 // A tile produced (4 warps)
+    uint64_t *bar_empty = bar_a + G_STAGES;                                             // MMAs of the stage retired
+    uint64_t *bar_acc = bar_empty + G_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_acc + 1);
+    float *prm = reinterpret_cast<float *>(smem + G_STAGES * G_STAGE_BYTES + 256);      // a_in c_in [H_in] | a_out c_out [H_out] | wf [NO][H_out]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * GM;
+    const int n_kb = P.kb_total;
+    const int Hi = P.H_in, Ho = P.H_out;
+    float *p_ain = prm, *p_cin = prm + Hi, *p_aout = prm + 2 * Hi, *p_cout = p_aout + Ho, *p_wf = p_cout + Ho;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_wh);
+        prefetch_tensormap(&map_wl);
+        for (int s = 0; s < G_STAGES; ++s) {
+            mbar_init(&bar_w[s], 1);
+            mbar_init(&bar_a[s], 2 * G_CONV_THREADS / 32);
+            mbar_init(&bar_empty[s], 1);
+        }
+        mbar_init(bar_acc, 1);
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < Hi; i += HT_THREADS) {
+        p_ain[i] = P.a_in[i];
+        p_cin[i] = P.c_in[i];
+    }
+    if (P.y != nullptr) {
+        for (int i = threadIdx.x; i < Ho; i += HT_THREADS) {
+            p_aout[i] = P.a_out[i];
+            p_cout[i] = P.c_out[i];
+        }
+        for (int i = threadIdx.x; i < P.NO * Ho; i += HT_THREADS) p_wf[i] = P.wf[i];
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * GN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < n_kb; ++i) {
+                const int s = i % G_STAGES;
+                const uint32_t ph = (uint32_t)(i / G_STAGES) & 1u;
+                mbar_wait(&bar_empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&bar_w[s], (uint32_t)(2 * G_B_BYTES));
+                tma_load_2d(s_wh(s), &map_wh, i * GK, 0, &bar_w[s]);
+                tma_load_2d(s_wl(s), &map_wl, i * GK, 0, &bar_w[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(GM, GN);
+            for (int i = 0; i < n_kb; ++i) {
+                const int s = i % G_STAGES;
+                const uint32_t ph = (uint32_t)(i / G_STAGES) & 1u;
+                mbar_wait(&bar_w[s], ph);
+                mbar_wait(&bar_a[s], ph);
+                tc_fence_after();
+                const uint64_t d_xh = umma_desc_sw128(s_xh(s)), d_xl = umma_desc_sw128(s_xl(s));
+                const uint64_t d_wh = umma_desc_sw128(s_wh(s)), d_wl = umma_desc_sw128(s_wl(s));
+#pragma unroll
+                for (int k = 0; k < GK / UK; ++k) {
+                    const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);
+                    const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
+                    umma_tf32(tmem_acc, d_xh + adv, d_wh + adv, idesc, first);
+                    umma_tf32(tmem_acc + GN, d_xl + adv, d_wh + adv, idesc, first);
+                    umma_tf32(tmem_acc + GN, d_xh + adv, d_wl + adv, idesc, 1u);
+                }
+                umma_commit(&bar_empty[s]);
+            }
+            umma_commit(bar_acc);
+        }
+        __syncwarp();
+    } else {
+        // ===== A producers (8 warps): thread = (sample row m of the CTA's 128, half of the K block's 32 features).  The
+        // loads of K block i + 1 (all splits, 64 registers) are in flight while block i is activated, split and stored.
+        const int pt = threadIdx.x - 64;
+        const int m = pt & (GM - 1), half = pt >> 7;
+        const long long blk = (long long)(m0 >> 5) + (m >> 5);
+        const bool row_ok = blk < P.MB;   // rows past the batch inside a valid block hold whatever the GEMM left there: finite
+        const float *src = P.in + ((blk * Hi) << 5) + lane;
+        const long long split_stride = ((long long)P.MB * Hi) << 5;
+        constexpr int HK = GK / 2, MAXS = 4;
+        // the next K block is in flight (registers) while the current one is split and stored.  (Two blocks in flight, 128
+        // more registers, measured no faster: the ring of two 96 KB operand stages sets the pace, not the load latency.)
+        float raw[MAXS][HK];
+        auto issue = [&](int i) {
+#pragma unroll
+            for (int sp = 0; sp < MAXS; ++sp)
+#pragma unroll
+                for (int j = 0; j < HK; ++j) {
+                    const int k = i * GK + half * HK + j;
+                    raw[sp][j] = (row_ok && sp < P.in_splits && k < Hi) ? __ldg(src + sp * split_stride + ((long long)k << 5)) : 0.f;
+                }
+        };
+        issue(0);
+#pragma unroll 1
+        for (int i = 0; i < n_kb; ++i) {
+            const int s = i % G_STAGES;
+            const uint32_t ph = (uint32_t)(i / G_STAGES) & 1u;
+            float v[HK];
+#pragma unroll
+            for (int j = 0; j < HK; ++j) {
+                float acc = raw[0][j];
+#pragma unroll
+                for (int sp = 1; sp < MAXS; ++sp) acc += raw[sp][j];
+                const int k = i * GK + half * HK + j;
+                v[j] = (row_ok && k < Hi) ? fmaxf(fmaf(acc, p_ain[k], p_cin[k]), 0.f) : 0.f;
+            }
+            if (i + 1 < n_kb) issue(i + 1);
+            mbar_wait(&bar_empty[s], ph ^ 1u);   // the MMAs that read this stage's previous tile have retired
+            unsigned char *xh = s_xh(s) + m * 128, *xl = s_xl(s) + m * 128;
+#pragma unroll
+            for (int cc = 0; cc < HK / 4; ++cc) {
+                const int c = half * (HK / 4) + cc;
+                float4 h, l;
+                h.x = tf32_hi(v[4 * cc + 0]);
+                h.y = tf32_hi(v[4 * cc + 1]);
+                h.z = tf32_hi(v[4 * cc + 2]);
+                h.w = tf32_hi(v[4 * cc + 3]);
+                l.x = v[4 * cc + 0] - h.x;
+                l.y = v[4 * cc + 1] - h.y;
+                l.z = v[4 * cc + 2] - h.z;
+                l.w = v[4 * cc + 3] - h.w;
+                const int pos = (c ^ (m & 7)) << 4;   // SWIZZLE_128B: 16-byte chunk c of row m sits at c ^ (m % 8)
+                *reinterpret_cast<float4 *>(xh + pos) = h;
+                *reinterpret_cast<float4 *>(xl + pos) = l;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_a[s]);
+        }
+        // ===== epilogue: thread = TMEM lane = sample row (warp w reads lanes [32 (w % 4), +32)); the two warps of a lane
+        // quadrant take alternate blocks of 32 columns and meet in shared memory for the output Linear
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const int q4 = warp & 3, cpar = (warp - 2) >> 2;
+        const int er = q4 * 32 + lane;            // row of the accumulator tile this thread reads
+        const long long b = (long long)m0 + er;
+        float yo[HT_MAX_NO];
+#pragma unroll
+        for (int o = 0; o < HT_MAX_NO; ++o) yo[o] = 0.f;
+        float *ocol = P.out ? P.out + (((((long long)(m0 >> 5) + q4) * Ho)) << 5) + lane : nullptr;
+#pragma unroll 1
+        for (int c = cpar; c < GN / 32; c += 2) {
+            if (c * 32 >= Ho) break;
+            uint32_t r[32], r2[32];
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(c * 32), r);
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(GN + c * 32), r2);
+            tmem_ld_wait();
+            if (P.y != nullptr) {
+                // this layer's BatchNorm + ReLU (layers.py:75-76), then the output Linear's dot products (layers.py:81)
+                float h2[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = c * 32 + j;
+                    h2[j] = n < Ho ? fmaxf(fmaf(__uint_as_float(r[j]) + __uint_as_float(r2[j]), p_aout[n], p_cout[n]), 0.f) : 0.f;
+                }
+#pragma unroll
+                for (int o = 0; o < HT_MAX_NO; ++o) {
+                    if (o < P.NO) {   // warp-uniform
+                        const float *wrow = p_wf + o * Ho + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c * 32 + j < Ho) yo[o] = fmaf(h2[j], wrow[j], yo[o]);
+                    }
+                }
+            } else if ((long long)(m0 >> 5) + q4 < P.MB) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c * 32 + j < Ho) ocol[(c * 32 + j) << 5] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+            }
+        }
+        if (P.y != nullptr) {
+            // the operand stages are idle now: odd-column warps hand their sums to the even-column warps
+            float *xch = reinterpret_cast<float *>(smem);   // [HT_MAX_NO][128]
+            if (cpar == 1) {
+#pragma unroll
+                for (int o = 0; o < HT_MAX_NO; ++o) xch[o * GM + er] = yo[o];
+            }
+            named_bar_sync(1, 2 * G_CONV_THREADS);
+            if (cpar == 0 && b < P.B) {
+#pragma unroll
+                for (int o = 0; o < HT_MAX_NO; ++o)
+                    if (o < P.NO) P.y[b * P.NO + o] = (yo[o] + xch[o * GM + er]) + __ldg(P.bf + o);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_acc, 2 * GN);
+}
+
 // ------------------------------------------------------------------ out-of-place transpose (training GEMM operands)
 // out[c][r] = in[r][c]; 64 x 64 tiles through shared memory, 16-byte global accesses on both sides when the shapes allow.
 // The backward of the first Linear needs x^T (134 MB at config 4); the generic strided copy reaches ~1.8 TB/s.
@@ -890,6 +1119,64 @@ int armnet_linear_tf32x3_dense(const float *x, int64_t B, int K, const float *w_
         return ARMNET_ERR_NULL;
     }
     return gemm_tf32x3_impl(x, B, K, w_hi, w_lo, N, 1, nullptr, y, bias, stream);
+}
+
+int armnet_mlp_hidden_tc_f32(const float *in_partials, int in_splits, int64_t B, int H_in, const float *a_in,
+                             const float *c_in, const float *w_hi, const float *w_lo, int H_out, const float *a_out,
+                             const float *c_out, const float *wf, const float *bf, int NO, float *y, float *out_partials,
+                             void *stream) {
+    if (!in_partials || !a_in || !c_in || !w_hi || !w_lo || (!y && !out_partials) ||
+        (y && (!a_out || !c_out || !wf || !bf))) {
+        set_error("armnet_mlp_hidden_tc_f32: null pointer");
+        return ARMNET_ERR_NULL;
+    }
+    if (B <= 0 || H_in <= 0 || H_out <= 0 || in_splits <= 0 || (y && NO <= 0)) {
+        set_error("armnet_mlp_hidden_tc_f32: bad sizes B=%lld H_in=%d H_out=%d splits=%d NO=%d", (long long)B, H_in, H_out,
+                  in_splits, NO);
+        return ARMNET_ERR_SHAPE;
+    }
+    if (H_out > GN || H_in > 1024 || (y && NO > HT_MAX_NO) || in_splits > 4) {
+        set_error("armnet_mlp_hidden_tc_f32: H_out <= %d, H_in <= 1024, outputs <= %d, splits <= 4 (got %d, %d, %d, %d)", GN,
+                  HT_MAX_NO, H_out, H_in, NO, in_splits);
+        return ARMNET_ERR_UNSUPPORTED;
+    }
+    if (H_in % 4 != 0 || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15)) {
+        set_error("armnet_mlp_hidden_tc_f32: TMA needs 16-byte aligned weight rows (H_in %% 4 == 0) and base pointers");
+        return ARMNET_ERR_ALIGN;
+    }
+    CUtensorMap mh, ml;
+    int rc;
+    if ((rc = make_map(&mh, w_hi, H_out, H_in, GN)) != ARMNET_OK) return rc;
+    if ((rc = make_map(&ml, w_lo, H_out, H_in, GN)) != ARMNET_OK) return rc;
+    HiddenParams P;
+    P.in = in_partials;
+    P.a_in = a_in;
+    P.c_in = c_in;
+    P.a_out = a_out;
+    P.c_out = c_out;
+    P.wf = wf;
+    P.bf = bf;
+    P.y = y;
+    P.out = y ? nullptr : out_partials;
+    P.B = B;
+    P.MB = (int)((B + 31) / 32);
+    P.in_splits = in_splits;
+    P.H_in = H_in;
+    P.H_out = H_out;
+    P.NO = y ? NO : 0;
+    P.kb_total = (H_in + GK - 1) / GK;
+    const int smem = G_STAGES * G_STAGE_BYTES + 1024 + 256 + (2 * H_in + 2 * H_out + HT_MAX_NO * H_out) * (int)sizeof(float);
+    DeviceInfo di;
+    if ((rc = get_device_info(&di)) != ARMNET_OK) return rc;
+    if (smem > di.smem_optin) {
+        set_error("armnet_mlp_hidden_tc_f32: %d bytes of shared memory needed (> %d)", smem, di.smem_optin);
+        return ARMNET_ERR_UNSUPPORTED;
+    }
+    ARMNET_CUDA_TRY(cudaFuncSetAttribute(mlp_hidden_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mlp_hidden_tc_kernel<<<(unsigned)((B + GM - 1) / GM), HT_THREADS, smem, (cudaStream_t)stream>>>(mh, ml, P);
+    ARMNET_CUDA_TRY(cudaGetLastError());
+    note_launches(1);
+    return ARMNET_OK;
 }
 
 size_t armnet_mlp_tail_packed_floats(int H, int n_rest, int NO) {

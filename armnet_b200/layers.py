@@ -64,6 +64,8 @@ class MLP(nn.Module):
         self.nhid = nhid
         self.tensor_core = True     # host-side knobs (not in state_dict)
         self.train_tensor_core = True   # training: first Linear's three GEMMs on tcgen05 (large batches only)
+        self.hidden_tensor_core = True  # eval: hidden layers 2..n + output Linear on tcgen05 (armnet_mlp_hidden_tc_f32)
+        self.hidden_tensor_core_min_batch = 512    # below it the CUDA-core tail kernel (one CTA per 32 samples) wins
         self._cache_key = None
         self._cache = None
 
@@ -82,15 +84,20 @@ class MLP(nn.Module):
             linears = [m for m in self.mlp if isinstance(m, nn.Linear)]
             bns = [m for m in self.mlp if isinstance(m, nn.BatchNorm1d)]
             w_hi, w_lo = ops.mlp_split_weight(linears[0].weight)
-            self._cache = (w_hi, w_lo, ops.mlp_pack_tail(linears, bns))
+            self._cache = (w_hi, w_lo, ops.mlp_pack_tail(linears, bns), ops.mlp_pack_layers(linears, bns))
             self._cache_key = key
         return self._cache
 
     def forward(self, x):
         if self._fast_ok(x):
-            w_hi, w_lo, packed = self._prepared()
+            w_hi, w_lo, packed, (ac, splits, last) = self._prepared()
+            B = x.shape[0]
             partials = ops.mlp_first_linear(x, w_hi, w_lo)
-            return ops.mlp_tail(partials, packed, self.nlayers - 1, self.noutput, x.shape[0])
+            if (self.hidden_tensor_core and self.nlayers >= 2 and B >= self.hidden_tensor_core_min_batch
+                    and self.nhid <= 256 and self.noutput <= 4 and partials.shape[0] <= 4):
+                # every further hidden Linear on tcgen05 too, fused with the activations around it and the output Linear
+                return ops.mlp_hidden_tc(partials, B, ac, splits, last)
+            return ops.mlp_tail(partials, packed, self.nlayers - 1, self.noutput, B)
         if (self.tensor_core and self.train_tensor_core and torch.is_grad_enabled() and x.is_cuda and x.dim() == 2
                 and x.dtype == torch.float32 and self.nlayers >= 1 and self.ninput % 4 == 0 and self.nhid % 4 == 0
                 and x.shape[0] % 4 == 0 and x.shape[0] >= 512 and self.ninput >= 1024):

@@ -394,6 +394,49 @@ def mlp_pack_tail(linears, bns):
         return torch.cat([p.reshape(-1).float() for p in parts]).contiguous()
 
 
+def mlp_pack_layers(linears, bns):
+    """Per-layer eval-mode parameters of the tensor-core hidden-layer path (armnet_mlp_hidden_tc_f32):
+    [(a_i, c_i)] for every hidden layer (a = bn.weight / sqrt(running_var + eps), c = (bias - running_mean) a + bn.bias),
+    [(w_hi, w_lo)] for hidden layers 2..n, and (wf, bf) of the output Linear."""
+    with torch.no_grad():
+        ac = []
+        for lin, bn in zip(linears[:-1], bns):
+            a = (bn.weight * torch.rsqrt(bn.running_var + bn.eps)).float().contiguous()
+            c = ((lin.bias - bn.running_mean) * a + bn.bias).float().contiguous()
+            ac.append((a, c))
+        splits = [mlp_split_weight(lin.weight) for lin in linears[1:-1]]
+        return ac, splits, (linears[-1].weight.detach().float().contiguous(), linears[-1].bias.detach().float().contiguous())
+
+
+def mlp_hidden_tc(partials, B, ac, splits, out):
+    """Hidden layers 2..n and the output Linear on tcgen05: one armnet_mlp_hidden_tc_f32 launch per hidden layer
+    (partials = split-K sums of layer 1, [S, ceil(B/32), H, 32]) -> y [B, noutput]."""
+    _need_cuda(partials)
+    wf, bf = out
+    NO = wf.shape[0]
+    MB = (B + 31) // 32
+    for l, (hi, lo) in enumerate(splits):
+        S, mb, H_in, _ = partials.shape
+        assert mb == MB and hi.shape[1] == H_in
+        H_out = hi.shape[0]
+        a_in, c_in = ac[l]
+        last = l == len(splits) - 1
+        if last:
+            y = torch.empty(B, NO, dtype=torch.float32, device=partials.device)
+            a_out, c_out = ac[l + 1]
+            check(lib.armnet_mlp_hidden_tc_f32(partials.data_ptr(), S, B, H_in, a_in.data_ptr(), c_in.data_ptr(),
+                                               hi.data_ptr(), lo.data_ptr(), H_out, a_out.data_ptr(), c_out.data_ptr(),
+                                               wf.data_ptr(), bf.data_ptr(), NO, y.data_ptr(), None, _stream()),
+                  'armnet_mlp_hidden_tc_f32')
+            return y
+        nxt = torch.empty(1, MB, H_out, 32, dtype=torch.float32, device=partials.device)
+        check(lib.armnet_mlp_hidden_tc_f32(partials.data_ptr(), S, B, H_in, a_in.data_ptr(), c_in.data_ptr(), hi.data_ptr(),
+                                           lo.data_ptr(), H_out, None, None, None, None, 0, None, nxt.data_ptr(),
+                                           _stream()), 'armnet_mlp_hidden_tc_f32')
+        partials = nxt
+    raise AssertionError('mlp_hidden_tc needs at least one hidden layer after the first')
+
+
 def partials_to_dense(partials, B):
     """[splits, MB, N, 32] partial sums -> the dense product [B, N] (test / validation helper)."""
     S, MB, N, _ = partials.shape

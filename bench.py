@@ -293,6 +293,8 @@ def main():
     ap.add_argument('--no-eager-leg', action='store_true', help='skip the reference-eager-on-GPU leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-flush', action='store_true', help='do not flush L2 between timed steps')
+    ap.add_argument('--no-hidden-tc', action='store_true',
+                    help='A/B: hidden layers 2..n of the MLP on the CUDA-core tail kernel instead of tcgen05')
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', '0'))
@@ -343,6 +345,8 @@ def main():
         torch.cuda.synchronize()
 
     model = build_module(w).to(dev).eval()
+    if args.no_hidden_tc:
+        model.mlp.hidden_tensor_core = False
     n_batches = 4
     host = [(i.pin_memory(), v.pin_memory()) for i, v in make_batches(w, n_batches, seed=1000 + rank)]
     resident = [(i.to(dev), v.to(dev)) for i, v in host]
@@ -429,7 +433,7 @@ def main():
     if rank == 0 and mlp_fast:
         with torch.no_grad():
             x_mlp = model.interaction({'id': resident[0][0], 'value': resident[0][1]}, fold_bn=True).reshape(w['bsz'], -1)
-            w_hi, w_lo, packed = model.mlp._prepared()
+            w_hi, w_lo, packed, (ac, hsplits, hout) = model.mlp._prepared()
 
             def ev_time(fn, n=20):
                 for _ in range(3):
@@ -446,6 +450,9 @@ def main():
             t_gemm = ev_time(lambda: ops.mlp_first_linear(x_mlp, w_hi, w_lo))
             part = ops.mlp_first_linear(x_mlp, w_hi, w_lo)
             t_tail = ev_time(lambda: ops.mlp_tail(part, packed, model.mlp.nlayers - 1, model.mlp.noutput, w['bsz']))
+            hidden_tc = (model.mlp.hidden_tensor_core and model.mlp.nlayers >= 2 and model.mlp.nhid <= 256
+                         and model.mlp.noutput <= 4 and w['bsz'] >= model.mlp.hidden_tensor_core_min_batch)
+            t_hidden = ev_time(lambda: ops.mlp_hidden_tc(part, w['bsz'], ac, hsplits, hout)) if hidden_tc else None
         flops = 3 * 2.0 * w['bsz'] * model.mlp.ninput * model.mlp.nhid         # three TF32 MMAs per fp32 product
         try:
             with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -458,7 +465,10 @@ def main():
                     'gemm_fp32_equivalent_tflops': flops / 3 / t_gemm / 1e12,
                     'roofline': {'bound': 'tensor', 'achieved': flops / t_gemm / 1e12, 'peak': tf32_peak,
                                  'unit': 'TFLOP/s', 'frac': flops / t_gemm / 1e12 / tf32_peak, 'peak_source': src},
-                    'tail_kernel_us': t_tail * 1e6}
+                    'tail_kernel_us': t_tail * 1e6,
+                    'hidden_tc_kernel_us': t_hidden * 1e6 if t_hidden is not None else None,
+                    'after_first_linear': ('mlp_hidden_tc_kernel (hidden layers 2..n + output Linear on tcgen05, 128 samples '
+                                           'per CTA)' if hidden_tc else 'mlp_tail_kernel (CUDA cores, 32 samples per CTA)')}
 
     eager = None
     if rank == 0 and world == 1 and not args.no_eager_leg:

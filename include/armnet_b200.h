@@ -209,6 +209,16 @@ int armnet_linear_tf32x3_dense(const float *x, int64_t B, int K, const float *w_
                                const float *bias, float *y, void *stream);
 /* out [cols, rows] = in [rows, cols]^T (tiled through shared memory); operands of the training GEMMs (x^T, W^T, dY^T). */
 int armnet_transpose_f32(const float *in, int64_t rows, int64_t cols, float *out, void *stream);
+/* One hidden layer after the first on the tensor cores, fused with the activation of its input and -- for the last
+ * hidden layer -- with its own BatchNorm/ReLU and the output Linear (layers.py:73-81, eval mode), 128 samples per CTA:
+ *   x = relu(sum_s in_partials[s] * a_in + c_in)  [B,H_in];   acc = x . w^T  (3xTF32 on tcgen05, w_hi / w_lo [H_out,H_in])
+ *   y != NULL:  y [B,NO] = relu(acc * a_out + c_out) . wf^T + bf     (wf [NO,H_out], NO <= 4)
+ *   y == NULL:  out_partials [1, ceil(B/32), H_out, 32] = acc         (input of the next call)
+ * H_out <= 256, in_splits <= 4, H_in % 4 == 0, else ARMNET_ERR_UNSUPPORTED / ARMNET_ERR_ALIGN (use armnet_mlp_tail_f32 then). */
+int armnet_mlp_hidden_tc_f32(const float *in_partials, int in_splits, int64_t B, int H_in, const float *a_in,
+                             const float *c_in, const float *w_hi, const float *w_lo, int H_out, const float *a_out,
+                             const float *c_out, const float *wf, const float *bf, int NO, float *y, float *out_partials,
+                             void *stream);
 size_t armnet_mlp_tail_packed_floats(int H, int n_rest, int NO);
 int armnet_mlp_tail_f32(const float *partials, int splits, int64_t B, int H, int n_rest, int NO, const float *packed,
                         float *y, void *stream);

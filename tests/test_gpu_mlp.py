@@ -80,6 +80,35 @@ def test_mlp_eval_fast_path_matches_stock_modules(ninput, nlayers, nhid, noutput
     assert nrel(y2, y2_ref) <= 1e-5
 
 
+@pytest.mark.parametrize('ninput,nlayers,nhid,noutput,B', [(5120, 2, 256, 1, 4096), (640, 3, 200, 1, 2049),
+                                                            (1280, 2, 252, 3, 1100), (5120, 3, 256, 1, 4100),
+                                                            (64, 2, 8, 4, 513)])
+def test_mlp_hidden_layers_on_tensor_cores(ninput, nlayers, nhid, noutput, B):
+    """Hidden layers 2..n + output Linear on tcgen05 (armnet_mlp_hidden_tc_f32, one launch per hidden layer) against the
+    fp64 evaluation of the stock modules and against the CUDA-core tail kernel; ragged batches, widths below 256."""
+    from armnet_b200.layers import MLP
+    torch.manual_seed(ninput + nhid + B)
+    m = MLP(ninput, nlayers, nhid, 0.1, noutput=noutput)
+    with torch.no_grad():
+        for mod in m.mlp:
+            if isinstance(mod, nn.BatchNorm1d):
+                mod.running_mean.normal_(0, 0.3)
+                mod.running_var.uniform_(0.5, 2.0)
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.normal_(0, 0.2)
+    m = m.to(dev()).eval()
+    x = torch.rand(B, ninput, device=dev()) * 2
+    with torch.no_grad():
+        assert m.hidden_tensor_core and B >= m.hidden_tensor_core_min_batch
+        y_tc = m(x)
+        m.hidden_tensor_core = False
+        y_tail = m(x)
+        y64 = m.double()(x.double())
+    e_tc, e_tail = nrel(y_tc, y64), nrel(y_tail, y64)
+    print(f'hidden layers on tcgen05: err vs fp64 {e_tc:.2e}; CUDA-core tail {e_tail:.2e}')
+    assert y_tc.shape == (B, noutput) and e_tc <= 1e-5 and e_tail <= 1e-5
+
+
 def test_mlp_train_mode_uses_stock_path():
     from armnet_b200.layers import MLP
     m = MLP(64, 2, 32, 0.0).to(dev()).train()

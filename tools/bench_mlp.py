@@ -46,7 +46,11 @@ with torch.no_grad():
     m.tensor_core = False
     t2 = timeit(lambda: m(x))
     m.tensor_core = True
-    w_hi, w_lo, packed = m._prepared()
+    w_hi, w_lo, packed, (ac, splits2, last) = m._prepared()
     part = ops.mlp_first_linear(x, w_hi, w_lo)
     t3 = timeit(lambda: ops.mlp_tail(part, packed, 1, 1, B))
-print(f'MLP eval forward: fast path {t1:.1f} us (tail kernel alone {t3:.1f} us), stock torch modules {t2:.1f} us')
+    print(f'MLP eval forward: fast path {t1:.1f} us (CUDA-core tail kernel alone {t3:.1f} us), stock torch modules {t2:.1f} us')
+    th = timeit(lambda: ops.mlp_hidden_tc(part, B, ac, splits2, last))
+    print(f'  hidden layer 2 + output on tcgen05 (armnet_mlp_hidden_tc_f32): {th:.1f} us; whole MLP {timeit(lambda: m(x)):.1f} us')
+    m.hidden_tensor_core = False
+    print(f'  whole MLP with the CUDA-core tail: {timeit(lambda: m(x)):.1f} us')

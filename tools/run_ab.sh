@@ -1,2 +1,6 @@
-for v in t0000 t11; do echo "== trace $v"; ARMNET_B200_LIB=$PWD/armnet_b200/tuning/lib$v.so python tools/trace_tmem.py --regime init 2>&1 | tail -24; done
-bash tools/ab_hot.sh base n0000 n1000 n0100 n1100 n1111
+timeout 300 python -m pytest tests/test_gpu_mlp.py -x -q -m gpu 2>&1 | tail -2
+timeout 200 python tools/bench_mlp.py 2>&1 | tail -3
+for i in 1 2; do
+python bench.py --no-train-leg --no-eager-leg --no-cpu-baseline --steps 50 --warmup 5 > gpurun_out/q_tc.json 2>/dev/null; python tools/show_bench.py gpurun_out/q_tc.json 2>/dev/null| head -1
+python bench.py --no-train-leg --no-eager-leg --no-cpu-baseline --steps 50 --warmup 5 --no-hidden-tc > gpurun_out/q_notc.json 2>/dev/null; python tools/show_bench.py gpurun_out/q_notc.json 2>/dev/null | head -1
+done
