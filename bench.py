@@ -524,7 +524,7 @@ def main():
                 'h2d_bytes_per_step': w['bsz'] * w['nfield'] * 12, 'd2h_bytes_per_step': w['bsz'] * 4,
                 'ms_per_step': e2e_s / args.steps * 1e3,
                 'what': 'armnet_b200.BatchScorer over pinned host batches: H2D ids+values, full ARMNetModel forward '
-                        '(fused kernel, tcgen05 MLP GEMM, tail kernel) as one CUDA graph per batch, D2H y; copies of '
+                        '(fused kernel, tcgen05 GEMM of the first Linear, tcgen05 hidden-layer + output kernel) as one CUDA graph per batch, D2H y; copies of '
                         'batch i+1 overlap the forward of batch i; 6 slots on 3 compute streams (the GEMM / tail of one batch overlaps the '
                         'fused kernel of the next)',
                 'per_call_sync': {'value': w['bsz'] * args.steps * n / e2e_sync_s, 'ms_per_step': e2e_sync_s / args.steps * 1e3,
