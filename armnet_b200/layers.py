@@ -46,9 +46,11 @@ class MLP(nn.Module):
     identical state_dict keys ('mlp.<i>.weight', ...).
 
     Eval mode without autograd on CUDA: the first Linear -- the one true GEMM of the path -- runs on the tcgen05
-    tensor cores (3xTF32 split, fp32 parity) and every layer after it in one CUDA-core kernel
-    (armnet_mlp_linear_tf32x3 / armnet_mlp_tail_f32). Training, or shapes TMA cannot address (ninput % 4 != 0),
-    use the stock torch modules (cuBLAS fp32)."""
+    tensor cores (3xTF32 split, fp32 parity; armnet_mlp_linear_tf32x3); the layers after it run on tcgen05 as well
+    (armnet_mlp_hidden_tc_f32: one launch per hidden layer, 128 samples per CTA, the last one fused with the output
+    Linear) when nhid <= 256, noutput <= 4 and the batch has >= 512 samples, else in one CUDA-core kernel
+    (armnet_mlp_tail_f32). Training, or shapes TMA cannot address (ninput % 4 != 0), use the stock torch modules
+    (cuBLAS fp32)."""
 
     def __init__(self, ninput, nlayers, nhid, dropout, noutput=1):
         super().__init__()
