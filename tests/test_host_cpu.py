@@ -139,6 +139,15 @@ def test_argument_validation_of_mlp_training_and_data_entries_without_gpu():
     assert lib.armnet_mlp_linear_tf32x3(p, 4, 6, p, p, 8, 1, p, None) == -5          # K % 4 != 0: TMA cannot address rows
     assert lib.armnet_mlp_tail_f32(p, 1, 4, 6, 0, 1, p, p, None) == -3               # H % 4 != 0
     assert lib.armnet_mlp_tail_f32(p, 1, 4, 1024, 0, 1, p, p, None) == -3            # H > 512
+    # armnet_mlp_hidden_tc_f32(in, splits, B, H_in, a_in, c_in, w_hi, w_lo, H_out, a_out, c_out, wf, bf, NO, y, out, stream)
+    assert lib.armnet_mlp_hidden_tc_f32(None, 1, 4, 8, p, p, p, p, 8, p, p, p, p, 1, p, None, None) == -1
+    assert lib.armnet_mlp_hidden_tc_f32(p, 1, 4, 8, p, p, p, p, 8, None, None, None, None, 0, None, None, None) == -1  # no output
+    assert lib.armnet_mlp_hidden_tc_f32(p, 1, 4, 8, p, p, p, p, 8, None, p, p, p, 1, p, None, None) == -1    # y without a_out
+    assert lib.armnet_mlp_hidden_tc_f32(p, 0, 4, 8, p, p, p, p, 8, p, p, p, p, 1, p, None, None) == -2       # splits < 1
+    assert lib.armnet_mlp_hidden_tc_f32(p, 1, 4, 8, p, p, p, p, 512, p, p, p, p, 1, p, None, None) == -3     # H_out > 256
+    assert lib.armnet_mlp_hidden_tc_f32(p, 5, 4, 8, p, p, p, p, 8, p, p, p, p, 1, p, None, None) == -3       # > 4 split-K slices
+    assert lib.armnet_mlp_hidden_tc_f32(p, 1, 4, 8, p, p, p, p, 8, p, p, p, p, 5, p, None, None) == -3       # > 4 outputs
+    assert lib.armnet_mlp_hidden_tc_f32(p, 1, 4, 6, p, p, p, p, 8, p, p, p, p, 1, p, None, None) == -5       # H_in % 4 != 0
     assert lib.armnet_clamp_adam_f32(p, p, p, p, 16, 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 0, None) == -2   # step < 1
     assert lib.armnet_clamp_adam_f32(None, p, p, p, 16, 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 1, None) == -1
     assert lib.armnet_bn_train_fwd_f32(p, 1, 4, 1, None, None, None, None, 0.1, 1e-5, p, p, p, p, None) == -2
