@@ -280,7 +280,25 @@ def cpu_reference_rate(w, state, steps, warmup, sample_b, full_model, seed=99):
     return sample_b * len(times) / total, total / len(times), cores
 
 
+_JSON_FD = None
+
+
+def emit_json(obj):
+    """The ONE JSON line of the contract goes to the process's original stdout; everything else a library writes to fd 1
+    (NCCL prints its version banner there) has been redirected to stderr by main()."""
+    line = (json.dumps(obj) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
@@ -319,13 +337,13 @@ def main():
         rate, sec, cores = cpu_reference_rate(w, st, steps, warm, sample_b, full_model=True)
         sample = (f'{steps} steps x {sample_b} samples of the same workload (full ARMNetModel.forward, eval), '
                   f'torch {torch.__version__} CPU, {cores} threads, {sec:.2f} s/step, cpu: {cpu_model_string()}')
-        print(json.dumps({
+        emit_json({
             'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'samples/s', 'n_gpus': args.gpus,
             'steps': steps, 'warmup': warm, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
             'cpu_baseline': {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': rate, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'gpu_launches': 0}))
+            'gpu_launches': 0})
         return
 
     # ------------------------------------------------------------------ this repo's CUDA arm
@@ -336,7 +354,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep NCCL's version banner off stdout: ONE JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # NCCL's version banner / warnings off stdout: ONE JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
@@ -553,7 +571,7 @@ def main():
                                    'sample': f'3 steps x {sample_b} samples of the same workload (hot path '
                                              f'only), oracle port on torch CPU, {cores} threads, {sec:.2f} s/step, '
                                              f'cpu: {cpu_model_string()}'}
-        print(json.dumps(out))
+        emit_json(out)
     if world > 1:
         dist.destroy_process_group()
 
