@@ -63,7 +63,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_partial_kernel(const float *__r
     }
 }
 
-// One warp per channel: fixed-order sum of the partials of its L positions over all CTAs, in double.
+// One CTA per channel: fixed-order sum of the partials of its L positions over all CTAs of the partial pass, in double.
+// (One WARP per channel left 512 warps walking 19 MB of partials in chains of L2 latencies: 33 us at config 4; a CTA per
+// channel has every load of a thread in flight at once.)  Thread t adds elements t, t + 256, ... in order, the warp sums
+// by shuffles and the eight warp sums are added in warp order: run-to-run deterministic.
 // mode 0: mean, invstd, running-stat update.   mode 1: sum_dy, sum_dy_xmu (for dweight / dbias and the apply pass).
 __global__ void __launch_bounds__(BN_THREADS) bn_finalize_kernel(const float *__restrict__ partial, const float *__restrict__ x,
                                                                 int n_cta, int C, int L, long long n, float eps,
@@ -72,19 +75,19 @@ __global__ void __launch_bounds__(BN_THREADS) bn_finalize_kernel(const float *__
                                                                 float *__restrict__ running_var,
                                                                 const float *__restrict__ invstd_in,
                                                                 float *__restrict__ raw_out) {
-    const int warp = (blockIdx.x * BN_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    __shared__ double red[2][BN_THREADS / 32];
+    const int warp = blockIdx.x;   // the channel
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (warp >= C) return;
     const int CL = C * L;
     double s1 = 0.0, s2 = 0.0;
     const int total = n_cta * L;
-    // eight independent loads in flight per lane (the loop is a chain of L2 latencies otherwise: 50 us for 19 MB of
-    // partials at config 4); the additions keep their fixed order
     constexpr int kU = 8;
-    for (int i0 = lane; i0 < total; i0 += 32 * kU) {
+    for (int i0 = threadIdx.x; i0 < total; i0 += BN_THREADS * kU) {
         float2 t[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const int i = i0 + 32 * u;
+            const int i = i0 + BN_THREADS * u;
             const int cta = i / L, l = i - cta * L;
             t[u] = i < total ? __ldg(reinterpret_cast<const float2 *>(partial) + (long long)cta * CL + warp * L + l)
                              : make_float2(0.f, 0.f);
@@ -100,7 +103,18 @@ __global__ void __launch_bounds__(BN_THREADS) bn_finalize_kernel(const float *__
         s1 += __shfl_xor_sync(0xffffffffu, s1, m);
         s2 += __shfl_xor_sync(0xffffffffu, s2, m);
     }
-    if (lane != 0) return;
+    if (lane == 0) {
+        red[0][wid] = s1;
+        red[1][wid] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    s1 = s2 = 0.0;
+#pragma unroll
+    for (int w = 0; w < BN_THREADS / 32; ++w) {
+        s1 += red[0][w];
+        s2 += red[1][w];
+    }
     if (mode == 0) {
         const double pivot = (double)x[(long long)warp * L];
         const double md = s1 / (double)n;
@@ -220,7 +234,7 @@ int armnet_bn_train_fwd_f32(const float *x, int64_t B, int C, int L, const float
     const bool v4 = (CL % 4 == 0) && (((uintptr_t)x | (uintptr_t)out) % 16 == 0);
     if (v4) bn_partial_kernel<4><<<n_cta, BN_THREADS, 0, st>>>(x, nullptr, nullptr, B, CL, L, rpc, 0, workspace);
     else bn_partial_kernel<1><<<n_cta, BN_THREADS, 0, st>>>(x, nullptr, nullptr, B, CL, L, rpc, 0, workspace);
-    bn_finalize_kernel<<<(C * 32 + BN_THREADS - 1) / BN_THREADS, BN_THREADS, 0, st>>>(
+    bn_finalize_kernel<<<C, BN_THREADS, 0, st>>>(
         workspace, x, n_cta, C, L, (long long)B * L, eps, momentum, 0, save_mean, save_invstd, running_mean, running_var, nullptr, nullptr);
     if (v4)
         bn_apply_kernel<4><<<n_cta, BN_THREADS, 0, st>>>(x, nullptr, save_mean, save_invstd, weight, bias, nullptr, nullptr,
@@ -252,7 +266,7 @@ int armnet_bn_train_bwd_f32(const float *x, const float *dy, int64_t B, int C, i
     const bool v4 = (CL % 4 == 0) && (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) % 16 == 0);
     if (v4) bn_partial_kernel<4><<<n_cta, BN_THREADS, 0, st>>>(x, dy, save_mean, B, CL, L, rpc, 1, workspace);
     else bn_partial_kernel<1><<<n_cta, BN_THREADS, 0, st>>>(x, dy, save_mean, B, CL, L, rpc, 1, workspace);
-    bn_finalize_kernel<<<(C * 32 + BN_THREADS - 1) / BN_THREADS, BN_THREADS, 0, st>>>(
+    bn_finalize_kernel<<<C, BN_THREADS, 0, st>>>(
         workspace, x, n_cta, C, L, (long long)B * L, 0.f, 0.f, 1, dbias, dweight, nullptr, nullptr, save_invstd, raw);
     const float inv_n = 1.f / (float)((long long)B * L);
     if (v4)
