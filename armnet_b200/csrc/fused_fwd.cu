@@ -133,7 +133,8 @@ static bool use_tmem_kernel(int F, int E, int R, int mode) {
     // (C2a: 33.6 M vs 28.1 M samples/s); at alpha = 2 / 1.5 (no MUFU in the solver) armnet_fwd_kernel wins
     // (C2b: 49.5 M vs 41.5 M).  tuning "tmem" = 1 forces it wherever the shape allows, 0 switches it off.
     if (tuning().tmem == 0 || mode == POW_BISECT || !tmem_shape_supported(F, E, R)) return false;
-    return tuning().tmem == 1 || mode == POW_GENERAL;
+    // nemb 11..16 (wide packed layout): opt-in until it measures faster than armnet_fwd_mma_kernel
+    return tuning().tmem == 1 || (mode == POW_GENERAL && E <= 10);
 }
 }  // namespace armnet
 

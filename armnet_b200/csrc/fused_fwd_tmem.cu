@@ -7,21 +7,22 @@
 namespace armnet {
 
 static const TmemInstance kTmemInstances[] = {
-    ARMNET_TMEM_INSTANCE(20, 1),  // 39 fields: Criteo shape (C2a / C2b)
-    ARMNET_TMEM_INSTANCE(20, 0),  // 40 fields
+    ARMNET_TMEM_INSTANCE(20, 1),       // 39 fields, nemb <= 10: Criteo shape (C2a / C2b)
+    ARMNET_TMEM_INSTANCE(20, 0),       // 40 fields
+    ARMNET_TMEM_INSTANCE_WIDE(20, 1),  // 39 fields, nemb 11..16 (config 4 shape)
+    ARMNET_TMEM_INSTANCE_WIDE(20, 0),
 };
 
-static const TmemInstance *select_tmem_instance(int F) {
+static const TmemInstance *select_tmem_instance(int F, int E) {
     for (const TmemInstance &I : kTmemInstances)
-        if (F == 2 * I.NP - (I.odd ? 1 : 0)) return &I;
+        if (F == 2 * I.NP - (I.odd ? 1 : 0) && E <= I.EL && (I.EL == kTmEL || E > kTmEL)) return &I;
     return nullptr;
 }
 
 bool tmem_shape_supported(int F, int E, int R) {
     // tensor memory: A operand (R/128 blocks x 32 columns) + 4 D slots of 2 samples x 2 NP fields
-    const TmemInstance *I = select_tmem_instance(F);
-    if (I == nullptr || E < 1 || E > kTmEL || R % 128 != 0 || R < 128 || (R / 128) * kTmKP + 4 * 4 * I->NP > 512)
-        return false;
+    const TmemInstance *I = E >= 1 ? select_tmem_instance(F, E) : nullptr;
+    if (I == nullptr || R % 128 != 0 || R < 128 || (R / 128) * tm_a_cols(I->EL) + 4 * 4 * I->NP > 512) return false;
     // shared memory (sm_100: 227 KB opt-in per CTA) with the shallowest gather ring
     TmemParams P;
     memset(&P, 0, sizeof(P));
@@ -35,34 +36,35 @@ bool tmem_shape_supported(int F, int E, int R) {
     return TmemSmem(I->NP, 2, P).total <= 232448;
 }
 
-// Workspace of the TMEM kernel: Apk floats [R/128][128][32], then Vpk float2 [R][vstr] (16-byte padded).
-static size_t tmem_apk_bytes(int R) { return (size_t)R * kTmKP * 4; }
-static size_t tmem_vpk_bytes(int F, int R) {
-    const TmemInstance *I = select_tmem_instance(F);
+// Workspace of the TMEM kernel: Apk floats [R/128][128][32 | 48], then Vpk float2 [R][vstr] (16-byte padded).
+static size_t tmem_apk_bytes(int R, int EL) { return (size_t)R * tm_a_cols(EL) * 4; }
+static size_t tmem_vpk_bytes(int F, int E, int R) {
+    const TmemInstance *I = select_tmem_instance(F, E);
     return (((size_t)R * (I->NP + 2) * 8) + 15) / 16 * 16;
 }
 size_t tmem_workspace_bytes(int F, int E, int R) {
     if (!tmem_shape_supported(F, E, R)) return 0;
-    return tmem_apk_bytes(R) + tmem_vpk_bytes(F, R);
+    return tmem_apk_bytes(R, select_tmem_instance(F, E)->EL) + tmem_vpk_bytes(F, E, R);
 }
 
-// Apk[(kb*128 + i)*32 + k]: TMEM lane i of A block kb is neuron r = 128 kb + i;
-//   k in [0,10): M'[x=k][r];  [10,20): M'[x=k-10][r];  [20,30): M'[x] - trunc_tf32(M'[x]);  30, 31: 0
+// Apk[(kb*128 + i)*KA + k]: TMEM lane i of A block kb is neuron r = 128 kb + i;  EL = 10, KA = 32 (EL = 16, KA = 48):
+//   k in [0,EL): M'[x=k][r];  [EL,2EL): M'[x=k-EL][r];  [2EL,3EL): M'[x] - trunc_tf32(M'[x]);  beyond: 0
 //   M'[x][r] = (alpha-1) * d_k^-0.5 * sum_y W[k,x,y] Q[k,o,y]   (armnet.py:33-34, entmax.py:42; one-head: W[x,y] = W_lin[y,x])
 // Vpk[r*vstr + j] = (V[r][2j], V[r][2j+1])                                                          (armnet.py:36)
 __global__ void attn_prepare_tmem_kernel(const float *__restrict__ W, const float *__restrict__ Q,
                                          const float *__restrict__ Vals, int lin_layout, int F, int E, int D, int O, int R,
-                                         int NP, int vstr, float scale, float am1, float *__restrict__ Apk,
+                                         int NP, int vstr, int EL, float scale, float am1, float *__restrict__ Apk,
                                          float *__restrict__ Vpk) {
-    const int nA = R * kTmKP;
+    const int KA = tm_a_cols(EL);
+    const int nA = R * KA;
     const int nV = R * vstr * 2;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nA + nV; idx += gridDim.x * blockDim.x) {
         if (idx < nA) {
-            const int k = idx & (kTmKP - 1), row = idx >> 5;
+            const int row = idx / KA, k = idx - row * KA;
             const int r = row;                            // = 128 kb + i
-            const int x = k < 10 ? k : (k < 20 ? k - 10 : k - 20);
+            const int x = k < EL ? k : (k < 2 * EL ? k - EL : k - 2 * EL);
             float a = 0.f;
-            if (k < 30 && x < E) {
+            if (k < 3 * EL && x < E) {
                 const int kh = r / O;
                 const float *q = Q + (long long)r * D;
                 if (lin_layout) {
@@ -72,7 +74,7 @@ __global__ void attn_prepare_tmem_kernel(const float *__restrict__ W, const floa
                     for (int y = 0; y < D; ++y) a = fmaf(w[y], q[y], a);
                 }
                 a = (a * scale) * am1;
-                if (k >= 20) a = a - __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+                if (k >= 2 * EL) a = a - __uint_as_float(__float_as_uint(a) & 0xffffe000u);
             }
             Apk[idx] = a;
         } else {
@@ -92,19 +94,19 @@ __global__ void attn_prepare_tmem_kernel(const float *__restrict__ W, const floa
 int tmem_prepare(const float *bilinear_w, const float *query, const float *att_values, int w_is_linear_layout, float am1,
                  int F, int E, int D, int K, int O, void *workspace, cudaStream_t st) {
     const int R = K * O;
-    const TmemInstance *I = select_tmem_instance(F);
+    const TmemInstance *I = select_tmem_instance(F, E);
     DeviceInfo di;
     int rc = get_device_info(&di);
     if (rc != ARMNET_OK) return rc;
     float *Apk = (float *)workspace;
-    float *Vpk = (float *)((char *)workspace + tmem_apk_bytes(R));
+    float *Vpk = (float *)((char *)workspace + tmem_apk_bytes(R, I->EL));
     const int vstr = I->NP + 2;
-    const int total = R * kTmKP + R * vstr * 2;
+    const int total = R * tm_a_cols(I->EL) + R * vstr * 2;
     int blocks = (total + 255) / 256;
     if (blocks > di.sm_count * 4) blocks = di.sm_count * 4;
     const float scale = (float)pow((double)D, -0.5);  // armnet.py:15
     attn_prepare_tmem_kernel<<<blocks, 256, 0, st>>>(bilinear_w, query, att_values, w_is_linear_layout, F, E, D, O, R, I->NP,
-                                                      vstr, scale, am1, Apk, Vpk);
+                                                      vstr, I->EL, scale, am1, Apk, Vpk);
     ARMNET_CUDA_TRY(cudaGetLastError());
     return ARMNET_OK;
 }
@@ -114,7 +116,7 @@ int tmem_launch(const char *who, const void *ids, int ids_i32, float *values, co
                 int clamp_inplace, const float *post_mean, const float *post_scale, const float *post_shift, float *out_z,
                 const void *workspace, int *err_flag, cudaStream_t st) {
     const int R = K * O;
-    const TmemInstance *I = select_tmem_instance(F);
+    const TmemInstance *I = select_tmem_instance(F, E);
     DeviceInfo di;
     int rc = get_device_info(&di);
     if (rc != ARMNET_OK) return rc;
@@ -124,7 +126,7 @@ int tmem_launch(const char *who, const void *ids, int ids_i32, float *values, co
     P.values = values;
     P.table = table;
     P.Apk = (const float *)workspace;
-    P.Vpk = (const float2 *)((const char *)workspace + tmem_apk_bytes(R));
+    P.Vpk = (const float2 *)((const char *)workspace + tmem_apk_bytes(R, I->EL));
     P.post_mean = post_mean;
     P.post_scale = post_scale;
     P.post_shift = post_shift;
@@ -148,7 +150,7 @@ int tmem_launch(const char *who, const void *ids, int ids_i32, float *values, co
     // rows per thread: 1 (logits in registers) by default.  tuning "tmem_rows" == 2 (needs K*O % 256 == 0): two rows per
     // thread, dense rows streamed from tensor memory -- +4 % in the init-weight regime (34.9 M vs 33.5 M samples/s at
     // C2a), -10 % with sparse gates (13.9 M vs 15.5 M), so it is not the default (profiles/r2_v3_summary.md)
-    const int NR = (R % 256 == 0 && tuning().tmem_rows == 2) ? 2 : 1;
+    const int NR = (R % 256 == 0 && tuning().tmem_rows == 2 && I->kernel2 != nullptr) ? 2 : 1;
     // gather look-ahead: as deep as the raw ring that fits (<= 16 tiles = 32 samples: the mbarrier block holds 32)
     int look = 16;
     for (; look >= 1; --look) {

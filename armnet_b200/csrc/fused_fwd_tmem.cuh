@@ -55,7 +55,14 @@ constexpr int kTmWarpGather = kTmConsumers, kTmWarpConvert = kTmConsumers + 1, k
 constexpr int kTmThreads = (kTmConsumers + 4) * 32;
 constexpr int kTmTiles = 4;                           // B-tile ring (tiles of 2 samples)
 constexpr int kTmKP = 32;                             // packed K (floats per operand row = 128 bytes)
-constexpr int kTmEL = 10;                             // embedding lanes of the packed layout
+constexpr int kTmEL = 10;                             // embedding lanes of the narrow packed layout (nemb <= 10)
+constexpr int kTmELWide = 16;                         // ... of the wide one (nemb <= 16)
+// Packed operands.  B row (128 bytes): EL = 10: [e0..9 | l0..9 | e0..9 | 0 0], EL = 16: [e0..15 | l0..15]  (l = e - trunc_tf32(e)).
+// A row: EL = 10: [M | M | m | 0 0] = 32 columns, four K = 8 steps against B floats 0, 8, 16, 24;
+//        EL = 16: [M | M | m]       = 48 columns, six steps against B floats 0, 8 (M e), 16, 24 (M l), 0, 8 (m e).
+__host__ __device__ constexpr int tm_a_cols(int el) { return el <= kTmEL ? 32 : 48; }
+__host__ __device__ constexpr int tm_k_steps(int el) { return tm_a_cols(el) / 8; }
+__host__ __device__ constexpr int tm_b_float(int el, int k) { return el <= kTmEL ? 8 * k : 8 * (k < 4 ? k : k - 4); }
 
 // Timeline trace (tuning builds only, -DARMNET_TMEM_TRACE): clock64() of CTA-local events, 64 slots per CTA.
 #ifdef ARMNET_TMEM_TRACE
@@ -204,14 +211,15 @@ __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__
 // NR = 2: a thread owns two rows (same TMEM lane of two A blocks) whose logits are streamed from tensor memory on every
 //         pass (entmax_stream.cuh): every shared-memory read of an embedding row feeds two rows -- the one-row mapping is
 //         bound by the shared-memory -> register return path -- and a D slot (2 blocks) lives until its units are done.
-template <int NP, bool ODD, int NR>
+template <int NP, bool ODD, int NR, int EL>
 __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __grid_constant__ TmemParams P) {
+    static_assert(EL == kTmEL || (EL == kTmELWide && NR == 1), "embedding lanes: 10 (both thread mappings) or 16 (one row per thread)");
+    constexpr int KA = tm_a_cols(EL), KSTEPS = tm_k_steps(EL);
     constexpr int NFP = 2 * NP;
     static_assert(NFP % 8 == 0 && 2 * NFP <= 256 && (2 * NFP) % 16 == 0, "two samples of NFP rows are the N of one MMA");
     static_assert(NP % 4 == 0 && (NP < 16 || NP >= 16), "tcgen05.ld shapes: one .x32 for 16 pairs, .x8 for every 4 more");
     constexpr int DSLOT = NR * 2 * NFP;  // TMEM columns of a D slot: NR A blocks (128 neurons each) x 2 samples x NFP fields
     constexpr int NSLOT = 4 / NR;        // D slots (A operand: <= 192 columns, D: 320)
-    constexpr int EL = kTmEL;
     extern __shared__ __align__(1024) unsigned char smem_tm[];
     unsigned char *smem = smem_tm;
     const TmemSmem L(NP, NR, P);
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
     const int F = P.F, E = P.E, R = P.R;
     const int NBLK = R >> 7;         // A blocks of 128 neurons
     const int IPT = NBLK / NR;       // items per tile (an item = NR blocks x 2 samples)
-    const int A_COLS = NBLK * kTmKP;
+    const int A_COLS = NBLK * KA;
     const int G = (int)gridDim.x;
     const int n_local = (P.n_tiles - (int)blockIdx.x + G - 1) / G;   // tiles blockIdx.x + t * G
     const EntmaxParams ep = P.ep;
@@ -284,15 +292,15 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
         const uint32_t taddr = tmem + ((uint32_t)(qa * 32) << 16);
 #pragma unroll 1
         for (int kb = 0; kb < NBLK; ++kb) {
-            const float4 *src = reinterpret_cast<const float4 *>(P.Apk + ((long long)kb * 128 + qa * 32 + lane) * kTmKP);
-            float4 v[8];
+            const float4 *src = reinterpret_cast<const float4 *>(P.Apk + ((long long)kb * 128 + qa * 32 + lane) * KA);
+            float4 v[KA / 4];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c);
+            for (int c = 0; c < KA / 4; ++c) v[c] = __ldg(src + c);
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
+            for (int c8 = 0; c8 < KA / 8; ++c8) {
                 const float4 a = v[2 * c8], b = v[2 * c8 + 1];
                 const float r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                tm_st8(taddr + (uint32_t)(kb * kTmKP + c8 * 8), r);
+                tm_st8(taddr + (uint32_t)(kb * KA + c8 * 8), r);
             }
             tm_st_wait();
             tm_fence_before();
@@ -423,9 +431,10 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
                         const int rs = rs0 + s;
                         const float4 *src = reinterpret_cast<const float4 *>(raw + rs * L.raw_sample_bytes + f * P.row_bytes);
                         const float v = vals[rs * L.fpad + f];
-                        float e[12], l[12];
+                        constexpr int EC4 = (EL + 3) / 4;   // 16-byte chunks of a gathered row
+                        float e[4 * EC4], l[4 * EC4];
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
+                        for (int c = 0; c < EC4; ++c) {
                             float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (c * 16 < P.row_bytes) q = src[c];
                             e[4 * c + 0] = q.x;
@@ -434,21 +443,29 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
                             e[4 * c + 3] = q.w;
                         }
 #pragma unroll
-                        for (int x = 0; x < 12; ++x) {
+                        for (int x = 0; x < 4 * EC4; ++x) {
                             e[x] = (x < EL && x < E) ? __fmul_rn(e[x], v) : 0.f;
                             l[x] = e[x] - trunc_tf32(e[x]);
                         }
                         const int n = s * NFP + f;
                         float4 *dst = reinterpret_cast<float4 *>(tile + n * 128);
                         const int sw = n & 7;
-                        dst[0 ^ sw] = make_float4(e[0], e[1], e[2], e[3]);
-                        dst[1 ^ sw] = make_float4(e[4], e[5], e[6], e[7]);
-                        dst[2 ^ sw] = make_float4(e[8], e[9], l[0], l[1]);
-                        dst[3 ^ sw] = make_float4(l[2], l[3], l[4], l[5]);
-                        dst[4 ^ sw] = make_float4(l[6], l[7], l[8], l[9]);
-                        dst[5 ^ sw] = make_float4(e[0], e[1], e[2], e[3]);
-                        dst[6 ^ sw] = make_float4(e[4], e[5], e[6], e[7]);
-                        dst[7 ^ sw] = make_float4(e[8], e[9], 0.f, 0.f);
+                        if constexpr (EL == kTmEL) {
+                            dst[0 ^ sw] = make_float4(e[0], e[1], e[2], e[3]);
+                            dst[1 ^ sw] = make_float4(e[4], e[5], e[6], e[7]);
+                            dst[2 ^ sw] = make_float4(e[8], e[9], l[0], l[1]);
+                            dst[3 ^ sw] = make_float4(l[2], l[3], l[4], l[5]);
+                            dst[4 ^ sw] = make_float4(l[6], l[7], l[8], l[9]);
+                            dst[5 ^ sw] = make_float4(e[0], e[1], e[2], e[3]);
+                            dst[6 ^ sw] = make_float4(e[4], e[5], e[6], e[7]);
+                            dst[7 ^ sw] = make_float4(e[8], e[9], 0.f, 0.f);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                dst[c ^ sw] = make_float4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
+                                dst[(4 + c) ^ sw] = make_float4(l[4 * c], l[4 * c + 1], l[4 * c + 2], l[4 * c + 3]);
+                            }
+                        }
                     }
                 }
             }
@@ -483,9 +500,9 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
 #pragma unroll
                     for (int j = 0; j < NR; ++j)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tm_mma_tf32_ts(d + (uint32_t)(j * 2 * NFP), tmem + (uint32_t)((h * NR + j) * kTmKP + k * 8),
-                                           db + (uint64_t)(k * 32 >> 4), idesc, (uint32_t)k);
+                        for (int k = 0; k < KSTEPS; ++k)
+                            tm_mma_tf32_ts(d + (uint32_t)(j * 2 * NFP), tmem + (uint32_t)((h * NR + j) * KA + k * 8),
+                                           db + (uint64_t)(tm_b_float(EL, k) * 4 >> 4), idesc, (uint32_t)k);
                     tm_commit(&d_full[slot]);
                 }
                 __syncwarp();
@@ -719,13 +736,22 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
                     const int sw = f & 7;
                     const float4 c0 = *reinterpret_cast<const float4 *>(row + ((0 ^ sw) << 4));
                     const float4 c1 = *reinterpret_cast<const float4 *>(row + ((1 ^ sw) << 4));
-                    const float2 c2 = *reinterpret_cast<const float2 *>(row + ((2 ^ sw) << 4));
                     const float2 w2 = splat2(w);
                     acc[0] = ffma2(w2, make_float2(c0.x, c0.y), acc[0]);     // s[x] += w_f e[f,x]  (armnet.py:86-87)
                     acc[1] = ffma2(w2, make_float2(c0.z, c0.w), acc[1]);
                     acc[2] = ffma2(w2, make_float2(c1.x, c1.y), acc[2]);
                     acc[3] = ffma2(w2, make_float2(c1.z, c1.w), acc[3]);
-                    acc[4] = ffma2(w2, c2, acc[4]);
+                    if constexpr (EL == kTmEL) {
+                        const float2 c2 = *reinterpret_cast<const float2 *>(row + ((2 ^ sw) << 4));
+                        acc[4] = ffma2(w2, c2, acc[4]);
+                    } else {
+                        const float4 c2 = *reinterpret_cast<const float4 *>(row + ((2 ^ sw) << 4));
+                        const float4 c3 = *reinterpret_cast<const float4 *>(row + ((3 ^ sw) << 4));
+                        acc[4] = ffma2(w2, make_float2(c2.x, c2.y), acc[4]);
+                        acc[5] = ffma2(w2, make_float2(c2.z, c2.w), acc[5]);
+                        acc[6] = ffma2(w2, make_float2(c3.x, c3.y), acc[6]);
+                        acc[7] = ffma2(w2, make_float2(c3.z, c3.w), acc[7]);
+                    }
                 };
                 auto cross = [&](int j, const float2 (&w)[1]) {
                     fma_field(2 * j, w[0].x);
@@ -803,11 +829,14 @@ __global__ void __launch_bounds__(kTmThreads, 1) armnet_fwd_tmem_kernel(const __
 struct TmemInstance {
     int NP;
     int odd;
+    int EL;                // embedding lanes of the packed layout: 10 (nemb <= 10) or 16 (nemb <= 16)
     const void *kernel;    // one row per thread, logits in registers
-    const void *kernel2;   // two rows per thread, logits streamed from tensor memory (needs K*O % 256 == 0)
+    const void *kernel2;   // two rows per thread, logits streamed from tensor memory (needs K*O % 256 == 0; EL = 10 only)
 };
-#define ARMNET_TMEM_INSTANCE(NP, ODD)                                               \
-    { NP, ODD, (const void *)&armnet_fwd_tmem_kernel<NP, (ODD) != 0, 1>,            \
-      (const void *)&armnet_fwd_tmem_kernel<NP, (ODD) != 0, 2> }
+#define ARMNET_TMEM_INSTANCE(NP, ODD)                                                      \
+    { NP, ODD, kTmEL, (const void *)&armnet_fwd_tmem_kernel<NP, (ODD) != 0, 1, kTmEL>,     \
+      (const void *)&armnet_fwd_tmem_kernel<NP, (ODD) != 0, 2, kTmEL> }
+#define ARMNET_TMEM_INSTANCE_WIDE(NP, ODD)                                                          \
+    { NP, ODD, kTmELWide, (const void *)&armnet_fwd_tmem_kernel<NP, (ODD) != 0, 1, kTmELWide>, nullptr }
 
 }  // namespace armnet
