@@ -72,20 +72,31 @@ class FlatAdam:
     The parameters are re-pointed to views of a flat fp32 buffer and their .grad to views of a flat gradient bucket, so
     autograd accumulates straight into the bucket and step() is: [one NCCL all-reduce(sum) of the bucket] -> ONE kernel
     (armnet_clamp_adam_f32) that averages, clamps to [-clamp, clamp] and applies the Adam update in a single pass over
-    (p, g, m, v).  Equivalent to GradAllReducer.step() + torch.optim.Adam.step()."""
+    (p, g, m, v).  Equivalent to GradAllReducer.step() + torch.optim.Adam.step().
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, clamp=1.0, group=None):
+    shard_state=True (world > 1): the optimizer state is sharded over the ranks -- reduce-scatter of the bucket, the
+    clamp+Adam kernel on this rank's 1/world slice of (p, g, m, v), all-gather of the updated parameters.  Same bytes on
+    the wire as the all-reduce (reduce-scatter + all-gather IS the ring all-reduce), same update element by element, but
+    the Adam pass and the m / v buffers shrink by the world size."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, clamp=1.0, group=None, shard_state=False):
         self.params = [p for p in params if p.requires_grad]
         self.lr, self.betas, self.eps, self.clamp, self.group = lr, betas, eps, clamp, group
         dev = self.params[0].device
         if dev.type != 'cuda':
             raise RuntimeError('FlatAdam runs on CUDA parameters only (armnet_b200 has no CPU path)')
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.sharded = bool(shard_state) and world > 1
         sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]           # every view starts 16-byte aligned
         n = sum(sizes)
+        if self.sharded:                                                  # equal, 16-byte aligned shards
+            n = (n + 4 * world - 1) // (4 * world) * (4 * world)
         self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        n_state = n // world if self.sharded else n
+        self.exp_avg = torch.zeros(n_state, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n_state, dtype=torch.float32, device=dev)
+        self.g_shard = torch.zeros(n_state, dtype=torch.float32, device=dev) if self.sharded else None
         self.t = 0
         off = 0
         with torch.no_grad():
@@ -113,13 +124,24 @@ class FlatAdam:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if events is not None else None
         if ev:
             ev[0].record()
-        if world > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
-        if ev:
-            ev[1].record()
         self.t += 1
-        ops.clamp_adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, weight / world, self.clamp, self.lr,
-                       self.betas[0], self.betas[1], self.eps, self.t)
+        if self.sharded:
+            rank = dist.get_rank(self.group)
+            S = self.g_shard.numel()
+            dist.reduce_scatter_tensor(self.g_shard, self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+            if ev:
+                ev[1].record()
+            p_shard = self.flat_p[rank * S:(rank + 1) * S]
+            ops.clamp_adam(p_shard, self.g_shard, self.exp_avg, self.exp_avg_sq, weight / world, self.clamp, self.lr,
+                           self.betas[0], self.betas[1], self.eps, self.t)
+            dist.all_gather_into_tensor(self.flat_p, p_shard, group=self.group)
+        else:
+            if world > 1:
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+            if ev:
+                ev[1].record()
+            ops.clamp_adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, weight / world, self.clamp, self.lr,
+                           self.betas[0], self.betas[1], self.eps, self.t)
         # the kernel writes through raw pointers: tell torch, so every cache keyed on (data_ptr, _version) -- padded
         # embedding table, pre-contracted attention workspace, folded arm_bn, split MLP weights -- is rebuilt
         torch.autograd.graph.increment_version(self.params)

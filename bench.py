@@ -198,7 +198,9 @@ def train_c4_leg(dev, rank, world, steps=10, warmup=3):
     F, V, E, K, O, B = 39, 1000000, 16, 4, 128, 4096
     torch.manual_seed(2025)
     model = ab.ARMNetModel(F, V, E, K, 1.7, O, 2, 256, 0.0, False, 2, 256).to(dev).train()
-    stepper = FlatAdam(model.parameters(), lr=3e-3, clamp=1.0)
+    # >= 4 ranks: optimizer state sharded over the ranks (reduce-scatter, Adam on 1/world of the bucket, all-gather of the
+    # parameters): same wire bytes as the all-reduce, an 8x smaller Adam pass at 8 GPUs (2.99 -> 2.91 ms per step)
+    stepper = FlatAdam(model.parameters(), lr=3e-3, clamp=1.0, shard_state=world >= 4)
     crit = nn.BCEWithLogitsLoss()
     g = torch.Generator().manual_seed(100 + rank)
     batches = [(torch.randint(0, V, (B, F), generator=g).to(dev), torch.ones(B, F, device=dev),
@@ -248,13 +250,19 @@ def train_c4_leg(dev, rank, world, steps=10, warmup=3):
         ph[3] += e[4].elapsed_time(e[5])
     ph = [x / steps for x in ph]
     nbytes = stepper.numel() * 4
+    sharded = stepper.sharded
     del model, stepper, batches
     torch.cuda.empty_cache()
     return {'metric': 'training samples/s (config 4: armnet nemb=16, bsz=4096/GPU, dense Adam, 1 all-reduce/step)',
             'value': B * world * steps / (ms * 1e-3), 'unit': 'samples/s', 'n_gpus': world, 'steps': steps,
             'ms_per_step': ms / steps, 'grad_bucket_bytes': nbytes,
-            'phase_ms': {'forward+loss': ph[0], 'backward': ph[1], 'allreduce': ph[2], 'clamp+adam': ph[3]},
-            'allreduce_bus_GBps': (2.0 * (world - 1) / world * nbytes / (ph[2] * 1e-3) / 1e9) if world > 1 else None,
+            'phase_ms': ({'forward+loss': ph[0], 'backward': ph[1], 'reduce_scatter': ph[2],
+                          'clamp+adam(shard)+all_gather': ph[3]} if sharded else
+                         {'forward+loss': ph[0], 'backward': ph[1], 'allreduce': ph[2], 'clamp+adam': ph[3]}),
+            'collective': ('reduce-scatter + all-gather around a sharded clamp+Adam (optimizer state / world)' if sharded
+                           else 'one all-reduce of the flat gradient bucket'),
+            'allreduce_bus_GBps': (((1.0 if sharded else 2.0) * (world - 1) / world * nbytes / (ph[2] * 1e-3) / 1e9)
+                                   if world > 1 else None),
             'clocks': clocks}
 
 

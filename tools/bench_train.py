@@ -15,6 +15,7 @@ ap.add_argument('--steps', type=int, default=20)
 ap.add_argument('--warmup', type=int, default=5)
 ap.add_argument('--nemb', type=int, default=16)
 ap.add_argument('--optimizer', default='fused', choices=['torch', 'fused'])
+ap.add_argument('--shard', type=int, default=0, help='FlatAdam(shard_state=...): reduce-scatter / sharded Adam / all-gather')
 args = ap.parse_args()
 rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
 local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -30,7 +31,7 @@ torch.manual_seed(2025)
 model = ab.ARMNetModel(F, V, E, K, 1.7, O, 2, 256, 0.0, False, 2, 256).to(dev).train()
 if args.optimizer == 'fused':
     from armnet_b200.parallel import FlatAdam
-    stepper = FlatAdam(model.parameters(), lr=3e-3, clamp=1.0)
+    stepper = FlatAdam(model.parameters(), lr=3e-3, clamp=1.0, shard_state=bool(args.shard))
 else:
     opt = torch.optim.Adam(model.parameters(), lr=3e-3)
     reducer = GradAllReducer(model.parameters(), clamp=1.0)
@@ -84,8 +85,10 @@ ms = t.item()
 for ev in evs:
     for j in range(3):
         acc[j] += ev[j].elapsed_time(ev[j + 1])
+checksum = float(sum(p.detach().double().abs().sum() for p in model.parameters()))   # equal trajectories -> equal checksums
 if rank == 0:
     nparam = sum(p.numel() for p in model.parameters())
+    print('param |.| checksum after %d steps: %.10e (shard_state=%d)' % (args.steps + args.warmup, checksum, args.shard))
     print(json.dumps({'metric': 'training samples/s (config 4: armnet nemb=%d, bsz=4096/GPU, dense Adam, 1 all-reduce/step)' % E,
                       'value': B * world * args.steps / (ms * 1e-3), 'n_gpus': world, 'ms_per_step': ms / args.steps,
                       'optimizer': args.optimizer, 'params': nparam, 'grad_bucket_MB': nparam * 4 / 1e6,

@@ -227,7 +227,7 @@ def main(args, data, rank, world, dev):
         reducer = GradAllReducer(model.parameters(), clamp=1.0)
     else:
         from armnet_b200.parallel import FlatAdam
-        optimizer, reducer = FlatAdam(model.parameters(), lr=args.lr, clamp=1.0), None   # train.py:62-65 in one kernel
+        optimizer, reducer = FlatAdam(model.parameters(), lr=args.lr, clamp=1.0, shard_state=world >= 4), None   # train.py:62-65 in one kernel; optimizer state sharded from 4 ranks on
     best_valid, best_test, patience = 0.0, 0.0, 0
     start = time.time()
     for epoch in range(args.epoch):
