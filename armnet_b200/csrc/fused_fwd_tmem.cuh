@@ -11,7 +11,9 @@
 //         A row = [ M0..M9 | M0..M9 | m0..m9 | 0 0 ],  B row = [ e0..e9 | l0..l9 | e0..e9 | 0 0 ]
 //     with m = M - trunc_tf32(M), l = e - trunc_tf32(e): the tensor core reads the top 19 bits of an fp32 operand, so
 //     sum_k A_k B_k = sum_x (M e + M l + m e) -- fp32-grade logits (5.6e-7 norm-relative on B200,
-//     tools/ubench/tmem_logits_check.cu) from ONE accumulation chain of 4 MMAs (~45 cycles each).
+//     tools/ubench/tmem_logits_check.cu) from ONE accumulation chain of 4 MMAs (~45 cycles each).  nemb 11..16 use the
+//     wide layout (EL = 16): B row = [ e0..e15 | l0..l15 ], A row = [ M | M | m ] in 48 columns, six K = 8 steps of which
+//     the last two re-read B floats 0..15 (tm_a_cols / tm_k_steps / tm_b_float below).
 //   * TMEM lane i of the D block of A-block kb is neuron 128 kb + i, so a thread reads ITS row's 40 logits with
 //     tcgen05.ld (fields packed in (f, f+1) register pairs -- the layout entmax_rows.cuh works on) and the D slot is
 //     released as soon as the registers are loaded (four slots: the MMAs of the next items run under the current entmax).
@@ -21,15 +23,20 @@
 //     e rows read (warp-broadcast) from the B tile itself -- its first 10 floats are the exact fp32 e --, exp, optional
 //     eval-mode arm_bn, one TMA bulk store per warp-unit (32 consecutive neurons x E of one sample).
 // Roles: 16 consumer warps (4 per TMEM lane quadrant; units = (item, quadrant, sample) taken in order from one counter
-// per quadrant) + three producer warps that only meet through mbarriers: the GATHER warp prefetches ids / values (clamp
-// in place, range check) and issues the TMA bulk row gathers up to 16 tiles ahead into a raw ring; the CONVERT warp turns
+// per quadrant) + three producer warps that only meet through mbarriers: the GATHER warp requests the ids / values of
+// tile t + 1 while it issues tile t (clamp in place and range check at use: it never waits for a load inside its loop) and
+// issues the TMA bulk row gathers up to 16 tiles ahead into a raw ring; the CONVERT warp turns
 // landed rows into B-tile rows (scale by the value: e = T[id] v exactly as layers.py:21; split; swizzled store); the MMA
 // warp issues the tcgen05.mma of an item the moment its tile is converted and a D slot is free (a single producer warp
 // doing all three in sequence starved the consumers: 28 % issue utilisation, profiles/r2_v3_summary.md).  No CTA-wide
 // barrier in steady state; every mbarrier wait is bounded (a protocol bug traps instead of hanging the device).
-// Requirements (host-checked, everything else runs on armnet_fwd_kernel): F in {2NP-1, 2NP} for a compiled NP, E <= 10,
-// K*O a multiple of 128 and <= 768 (tensor-memory columns), 16-byte-aligned table rows (the module's padded shadow
-// table), no validation outputs, solver != literal bisection.
+// Start-up (tools/trace_tmem.py, -DARMNET_TMEM_TRACE): consumer warps 0-3 put M'^T into tensor memory block by block
+// (the first MMA needs block 0), the first logits appear ~7 us after CTA entry (ids 1 us, 78 bulk copies 2.3 us to issue,
+// rows 0.8 us, convert 0.7 us); the ring indices and the item -> tile index carry no runtime division.
+// Requirements (host-checked, everything else runs on armnet_fwd_kernel / armnet_fwd_mma_kernel): F in {2NP-1, 2NP} for a
+// compiled NP, E <= 16 (E > 10: opt-in, tuning tmem = 1), K*O a multiple of 128 with (K*O / 128) * (32 | 48) + 320 <= 512
+// tensor-memory columns, 16-byte-aligned table rows (the module's padded shadow table), no validation outputs,
+// solver != literal bisection.
 #pragma once
 
 #include "entmax_rows.cuh"
