@@ -187,7 +187,12 @@ def test_fused_kernel_selection_is_host_logic():
         assert ops.fused_fwd_kernel_kind(39, 10, 4, 64, 2.0) == 3        # forced on
         assert ops.fused_fwd_kernel_kind(40, 8, 2, 128, 1.0) == 3
         assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 2.5) == 1       # never with the literal bisection
+        assert ops.fused_fwd_kernel_kind(39, 16, 4, 128, 1.7) == 3       # nemb 16: wide packed layout, opt-in
+        assert ops.fused_fwd_kernel_kind(40, 13, 2, 128, 1.7) == 3
+        assert ops.fused_fwd_kernel_kind(39, 16, 5, 128, 1.7) != 3       # 5 x 48 + 320 tensor-memory columns > 512
+        assert ops.fused_fwd_kernel_kind(39, 17, 4, 128, 1.7) != 3       # nemb > 16
         ops.set_tuning('tmem', -1)
+        assert ops.fused_fwd_kernel_kind(39, 16, 4, 128, 1.7) == 2       # default at nemb 16: armnet_fwd_mma_kernel
         assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 2.5) == 1       # alpha > 2 -> literal bisection
         assert ops.fused_fwd_kernel_kind(39, 10, 4, 128, 1.7, ops.SOLVER_BISECT) == 1
         assert ops.fused_fwd_kernel_kind(39, 10, 4, 100, 1.7) == 1       # K*O % 256 != 0
