@@ -86,7 +86,7 @@ class FlatAdam:
         if dev.type != 'cuda':
             raise RuntimeError('FlatAdam runs on CUDA parameters only (armnet_b200 has no CPU path)')
         world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.sharded = bool(shard_state) and world > 1
+        self.sharded = bool(shard_state) and world > 1     # any true value; callers pass `world >= 4` (measured break-even)
         sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]           # every view starts 16-byte aligned
         n = sum(sizes)
         if self.sharded:                                                  # equal, 16-byte aligned shards

@@ -292,3 +292,45 @@ def test_eval_caches_follow_flat_adam_and_bn_updates():
     y_ref = eval_once(fresh)
     assert (y1 - y2).abs().max().item() > 1e-4, 'training did not move the output: the test is vacuous'
     assert torch.allclose(y2, y_ref, rtol=1e-6, atol=1e-6), (y2 - y_ref).abs().max().item()
+
+
+def _sharded_adam_worker(rank, world, port, out):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    d = torch.device('cuda', rank)
+    dist.init_process_group('nccl', device_id=d)
+    from armnet_b200.parallel import FlatAdam
+    res = {}
+    for shard in (False, True):
+        torch.manual_seed(5)
+        net = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.ReLU(), torch.nn.Linear(19, 3)).to(d)   # odd sizes: padding
+        opt = FlatAdam(net.parameters(), lr=1e-2, clamp=0.05, shard_state='force' if shard else False)
+        assert opt.sharded == shard
+        g = torch.Generator().manual_seed(100 + rank)
+        for _ in range(4):
+            x = torch.randn(16, 37, generator=g).to(d)
+            opt.zero_grad()
+            net(x).square().mean().backward()
+            opt.step()
+        res[shard] = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu()
+        if shard:
+            assert opt.exp_avg.numel() * world == opt.flat_p.numel()      # the state really is 1 / world per rank
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (NCCL reduce-scatter / all-gather)')
+def test_flat_adam_sharded_state_matches_all_reduce(tmp_path):
+    """FlatAdam(shard_state=...): reduce-scatter + Adam on 1/world of the bucket + all-gather gives the parameters of the
+    all-reduce + full Adam path (two ranks, different data per rank, gradient clamp active, bucket size not a multiple of
+    the world size)."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'res.pt')
+    mp.spawn(_sharded_adam_worker, args=(2, 29577, out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert torch.allclose(res[False], res[True], rtol=0, atol=1e-7)
+    assert not torch.equal(res[False], torch.zeros_like(res[False]))
