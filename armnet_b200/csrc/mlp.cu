@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1)
         const int pt = threadIdx.x - 64;
         const int m = pt & (GM - 1), half = pt >> 7;
         const long long blk = (long long)(m0 >> 5) + (m >> 5);
-        const bool row_ok = blk < P.MB;   // rows past the batch inside a valid block hold whatever the GEMM left there: finite
+        const bool row_ok = (long long)m0 + m < P.B;   // rows past the batch are never read (the GEMM does not write them): zeros
         const float *src = P.in + ((blk * Hi) << 5) + lane;
         const long long split_stride = ((long long)P.MB * Hi) << 5;
         constexpr int HK = GK / 2, MAXS = 4;
