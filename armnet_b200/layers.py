@@ -68,6 +68,7 @@ class MLP(nn.Module):
         self.train_tensor_core = True   # training: first Linear's three GEMMs on tcgen05 (large batches only)
         self.hidden_tensor_core = True  # eval: hidden layers 2..n + output Linear on tcgen05 (armnet_mlp_hidden_tc_f32)
         self.hidden_tensor_core_min_batch = 512    # below it the CUDA-core tail kernel (one CTA per 32 samples) wins
+        self.first_splits = None        # split-K slices of the first Linear's GEMM (None: armnet_mlp_linear_splits)
         self._cache_key = None
         self._cache = None
 
@@ -94,7 +95,7 @@ class MLP(nn.Module):
         if self._fast_ok(x):
             w_hi, w_lo, packed, (ac, splits, last) = self._prepared()
             B = x.shape[0]
-            partials = ops.mlp_first_linear(x, w_hi, w_lo)
+            partials = ops.mlp_first_linear(x, w_hi, w_lo, splits=self.first_splits)
             if (self.hidden_tensor_core and self.nlayers >= 2 and B >= self.hidden_tensor_core_min_batch
                     and self.nhid <= 256 and self.noutput <= 4 and partials.shape[0] <= 4):
                 # every further hidden Linear on tcgen05 too, fused with the activations around it and the output Linear

@@ -8,6 +8,8 @@ w = bench.WORKLOADS['c2a']
 dev = torch.device('cuda:0')
 model = bench.build_module(w).to(dev).eval()
 host = [(i.pin_memory(), v.pin_memory()) for i, v in bench.make_batches(w, 8, seed=3)]
+import sys as _s
+model.mlp.first_splits = int(_s.argv[1]) if len(_s.argv) > 1 else None   # optional: split-K slices of the first Linear
 for depth, streams in ((6, 3), (4, 2), (8, 4), (8, 2), (9, 3), (12, 4), (2, 1)):
     scorer = BatchScorer(model, w['bsz'], w['nfield'], depth=depth, compute_streams=streams)
     def run(steps):
